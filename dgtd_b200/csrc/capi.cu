@@ -1,0 +1,572 @@
+// C ABI of libdgtd_b200.so (include/dgtd_b200.h): contexts, device memory, launches, halo exchange.
+// Host logic mirrors what the reference does around its operator:
+//   Mult        src/evolution/GlobalEvolution.cpp:628-823   (halo exchange -> operator -> TF/SF injection)
+//   RK4 step    external/mfem-geg/linalg/ode.cpp:109-136     (fused here: 4 launches, no k vector, no AXPY passes)
+//   time loop   src/solver/Solver.cpp:483-551
+// There is no CPU path in this file: every compute entry point needs a CUDA device.
+#include "../../include/dgtd_b200.h"
+#include "host.hpp"
+#include "kernels.cuh"
+
+#include <dlfcn.h>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+using namespace dgtd;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                                                   \
+    do {                                                                                                           \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess) throw Error(DGTD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
+    } while (0)
+
+#define GUARD_BEGIN try {
+#define GUARD_END                                                                       \
+    }                                                                                   \
+    catch (const Error &e) { return fail(e.code, e.what()); }                           \
+    catch (const std::bad_alloc &) { return fail(DGTD_ERR_ARG, "out of host memory"); } \
+    catch (const std::exception &e) { return fail(DGTD_ERR_ARG, e.what()); }            \
+    return DGTD_OK;
+
+struct dgtd_mesh { Mesh m; };
+
+// ---- minimal NCCL binding, resolved at run time from the libnccl.so.2 already in the process (torch's) -------------
+namespace {
+typedef struct ncclComm *ncclComm_t;
+struct NcclId { char internal[128]; };
+struct Nccl {
+    void *h = nullptr;
+    int (*GetUniqueId)(NcclId *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    void load()
+    {
+        if (h) return;
+        h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) throw Error(DGTD_ERR_COMM, std::string("cannot load libnccl.so.2: ") + dlerror());
+        auto sym = [&](const char *n) { void *p = dlsym(h, n); if (!p) throw Error(DGTD_ERR_COMM, std::string("missing NCCL symbol ") + n); return p; };
+        GetUniqueId = (decltype(GetUniqueId))sym("ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))sym("ncclCommInitRank");
+        CommDestroy = (decltype(CommDestroy))sym("ncclCommDestroy");
+        GroupStart = (decltype(GroupStart))sym("ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))sym("ncclGroupEnd");
+        Send = (decltype(Send))sym("ncclSend");
+        Recv = (decltype(Recv))sym("ncclRecv");
+        GetErrorString = (decltype(GetErrorString))sym("ncclGetErrorString");
+    }
+    void check(int r, const char *what) { if (r != 0) throw Error(DGTD_ERR_COMM, std::string(what) + ": " + (GetErrorString ? GetErrorString(r) : "nccl error")); }
+};
+Nccl g_nccl;
+constexpr int NCCL_FLOAT64 = 8;   // ncclDouble
+}  // namespace
+
+template <class T> struct DevBuf {
+    T *p = nullptr; size_t n = 0;
+    void alloc(size_t count) { release(); n = count; if (count) CU(cudaMalloc(&p, count * sizeof(T))); }
+    void upload(const std::vector<T> &h, size_t padTo = 0)
+    {
+        alloc(std::max(h.size(), padTo));
+        if (n) CU(cudaMemset(p, 0, n * sizeof(T)));
+        if (!h.empty()) CU(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { release(); }
+};
+
+typedef void (*StageFn)(const StageArgs);
+struct KernelSet { StageFn fn[4]; int threads; size_t smem; };
+
+template <int DIM, int P> static KernelSet kset()
+{
+    using E = Elem<DIM, P>;
+    return {{stage_kernel<DIM, P, 0>, stage_kernel<DIM, P, 1>, stage_kernel<DIM, P, 2>, stage_kernel<DIM, P, 3>}, E::T, E::smem_bytes};
+}
+static KernelSet select_kernels(int dim, int p)
+{
+    switch (dim * 10 + p) {
+        case 11: return kset<1, 1>(); case 12: return kset<1, 2>(); case 13: return kset<1, 3>();
+        case 14: return kset<1, 4>(); case 15: return kset<1, 5>(); case 16: return kset<1, 6>();
+        case 21: return kset<2, 1>(); case 22: return kset<2, 2>(); case 23: return kset<2, 3>();
+        case 24: return kset<2, 4>(); case 25: return kset<2, 5>(); case 26: return kset<2, 6>();
+        case 31: return kset<3, 1>(); case 32: return kset<3, 2>(); case 33: return kset<3, 3>();
+        case 34: return kset<3, 4>(); case 35: return kset<3, 5>();
+    }
+    throw Error(DGTD_ERR_UNSUPPORTED, "no kernel for this dimension/order");
+}
+
+struct dgtd_ctx {
+    HostOp H;
+    Mesh mesh;                       // kept for node_coords
+    int device = 0;
+    int rank = 0, nranks = 1;
+    long long Nloc = 0, Nglob = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    KernelSet ks{};
+    int grid = 0;
+    DevBuf<double> D, LIFT, geo, tfsf_xyz, gate_xyz, gate, x, ya, yb, z, halo, sendbuf, scratch, tmp_in, tmp_out;
+    DevBuf<int> finfo, send_node;
+    DevBuf<uint8_t> ftab;
+    DevPlaneWave pw{};
+    int pw_on = 0;
+    ncclComm_t comm = nullptr;
+    long long launches = 0;
+    std::vector<double> hostbuf;     // pinned staging would go here; plain vector for gather/scatter by element
+    ~dgtd_ctx()
+    {
+        if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+        if (own_stream) cudaStreamDestroy(own_stream);
+    }
+};
+
+static void fill_args(dgtd_ctx *c, StageArgs &A)
+{
+    A.D = c->D.p; A.LIFT = c->LIFT.p; A.geo = c->geo.p; A.finfo = reinterpret_cast<const int2 *>(c->finfo.p);
+    A.ftab = c->ftab.p; A.tfsf_xyz = c->tfsf_xyz.p; A.gate = nullptr; A.halo = c->halo.p;
+    A.NE = c->H.NEloc; A.stride = c->Nloc; A.hstride = (long long)c->H.n_halo_faces * c->H.Nfp;
+    A.alpha = c->H.alpha; A.pw = c->pw; A.pw_on = c->pw_on;
+}
+
+// halo exchange of the face traces of `y` (GlobalEvolution.cpp:763-774 ships whole neighbour elements, 6 blocking
+// MPI exchanges; here one packed NCCL group per RHS evaluation)
+static void exchange(dgtd_ctx *c, const double *y)
+{
+    if (c->nranks == 1 || c->H.n_halo_faces == 0) return;
+    if (!c->comm) throw Error(DGTD_ERR_COMM, "multi-rank context used before dgtd_comm_init");
+    const int Nfp = c->H.Nfp;
+    const int ns = c->H.n_halo_faces * Nfp;
+    pack_kernel<<<std::min(1024, (ns + 255) / 256), 256, 0, c->stream>>>(y, c->Nloc, c->send_node.p, ns, c->sendbuf.p, ns);
+    c->launches++;
+    g_nccl.check(g_nccl.GroupStart(), "ncclGroupStart");
+    for (auto &pp : c->H.peers)
+        for (int comp = 0; comp < 6; comp++) {
+            const size_t off = (size_t)comp * ns + (size_t)pp.send_off * Nfp, cnt = (size_t)pp.nfaces * Nfp;
+            g_nccl.check(g_nccl.Send(c->sendbuf.p + off, cnt, NCCL_FLOAT64, pp.rank, c->comm, c->stream), "ncclSend");
+            g_nccl.check(g_nccl.Recv(c->halo.p + off, cnt, NCCL_FLOAT64, pp.rank, c->comm, c->stream), "ncclRecv");
+        }
+    g_nccl.check(g_nccl.GroupEnd(), "ncclGroupEnd");
+}
+
+static void launch_gate(dgtd_ctx *c, const double *ts, int nt)
+{
+    CU(cudaMemsetAsync(c->gate.p, 0, 4 * sizeof(double), c->stream));
+    const int V = (int)(c->H.gate_xyz.size() / 3);
+    gate_kernel<<<std::min(296, (V + 255) / 256), 256, 0, c->stream>>>(c->gate_xyz.p, V, c->pw, ts[0], ts[1], ts[2], ts[3], nt, c->gate.p);
+    c->launches++;
+}
+
+static void launch_stage(dgtd_ctx *c, int mode, StageArgs &A)
+{
+    exchange(c, A.yin);
+    c->ks.fn[mode]<<<c->grid, c->ks.threads, c->ks.smem, c->stream>>>(A);
+    c->launches++;
+    CU(cudaGetLastError());
+}
+
+static void rk4_step(dgtd_ctx *c, double t, double dt)
+{
+    StageArgs A; fill_args(c, A);
+    const bool gated = c->pw_on && c->H.tfsf_gate;
+    if (gated) { double ts[4] = {t, t + dt / 2, t + dt, 0}; launch_gate(c, ts, 3); }
+    // k1 = f(t, x); y = x + dt/2 k1; z = x + dt/6 k1
+    A.yin = c->x.p; A.x = c->x.p; A.z = c->z.p; A.yout = c->ya.p; A.a = dt / 2; A.b = dt / 6; A.t = t; A.gate = gated ? c->gate.p + 0 : nullptr;
+    launch_stage(c, MODE_STAGE1, A);
+    // k2 = f(t + dt/2, y); y = x + dt/2 k2; z += dt/3 k2
+    A.yin = c->ya.p; A.yout = c->yb.p; A.a = dt / 2; A.b = dt / 3; A.t = t + dt / 2; A.gate = gated ? c->gate.p + 1 : nullptr;
+    launch_stage(c, MODE_STAGE23, A);
+    // k3 = f(t + dt/2, y)  (time not advanced, ode.cpp:127); y = x + dt k3; z += dt/3 k3
+    A.yin = c->yb.p; A.yout = c->ya.p; A.a = dt; A.b = dt / 3;
+    launch_stage(c, MODE_STAGE23, A);
+    // k4 = f(t + dt, y); x = z + dt/6 k4
+    A.yin = c->ya.p; A.yout = c->x.p; A.b = dt / 6; A.t = t + dt; A.gate = gated ? c->gate.p + 2 : nullptr;
+    launch_stage(c, MODE_STAGE4, A);
+}
+
+static void mult_device(dgtd_ctx *c, double t, const double *in, double *out)
+{
+    if (in == out) throw Error(DGTD_ERR_ARG, "Mult: in and out must not alias");
+    StageArgs A; fill_args(c, A);
+    const bool gated = c->pw_on && c->H.tfsf_gate;
+    if (gated) { double ts[4] = {t, 0, 0, 0}; launch_gate(c, ts, 1); }
+    A.yin = in; A.x = in; A.z = nullptr; A.yout = out; A.a = 0; A.b = 0; A.t = t; A.gate = gated ? c->gate.p : nullptr;
+    launch_stage(c, MODE_MULT, A);
+}
+
+// global [6N] host vector <-> local [6][Nloc] device vector
+static void scatter_to_device(dgtd_ctx *c, const double *host, double *dev)
+{
+    const int Np = c->H.Np; const long long Ng = c->Nglob, Nl = c->Nloc;
+    if (c->nranks == 1) {   // identity element order
+        CU(cudaMemcpyAsync(dev, host, sizeof(double) * 6 * Nl, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        return;
+    }
+    c->hostbuf.resize((size_t)6 * Nl);
+    for (int comp = 0; comp < 6; comp++)
+        for (int le = 0; le < c->H.NEloc; le++)
+            std::memcpy(&c->hostbuf[(size_t)comp * Nl + (size_t)le * Np], host + (size_t)comp * Ng + (size_t)c->H.elem_gid[le] * Np, sizeof(double) * Np);
+    CU(cudaMemcpyAsync(dev, c->hostbuf.data(), sizeof(double) * 6 * Nl, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+}
+static void gather_from_device(dgtd_ctx *c, const double *dev, double *host)
+{
+    const int Np = c->H.Np; const long long Ng = c->Nglob, Nl = c->Nloc;
+    if (c->nranks == 1) {
+        CU(cudaMemcpyAsync(host, dev, sizeof(double) * 6 * Nl, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        return;
+    }
+    c->hostbuf.resize((size_t)6 * Nl);
+    CU(cudaMemcpyAsync(c->hostbuf.data(), dev, sizeof(double) * 6 * Nl, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int comp = 0; comp < 6; comp++)
+        for (int le = 0; le < c->H.NEloc; le++)
+            std::memcpy(host + (size_t)comp * Ng + (size_t)c->H.elem_gid[le] * Np, &c->hostbuf[(size_t)comp * Nl + (size_t)le * Np], sizeof(double) * Np);
+}
+
+static Options options_from_c(const dgtd_mesh *mesh, const dgtd_options *o)
+{
+    Options op;
+    op.order = o->order; op.alpha = o->alpha; op.rank = o->rank; op.nranks = o->nranks < 1 ? 1 : o->nranks; op.tfsf_gate = o->tfsf_gate != 0;
+    if ((o->n_bdr && (!o->bdr_attr || !o->bdr_cond)) || (o->n_tfsf && !o->tfsf_attr) || (o->n_mat && (!o->mat_attr || !o->mat_eps_mu_sigma)))
+        throw Error(DGTD_ERR_ARG, "dgtd_create: option arrays missing");
+    for (int i = 0; i < o->n_bdr; i++) op.bdr.push_back({o->bdr_attr[i], o->bdr_cond[i]});
+    for (int i = 0; i < o->n_tfsf; i++) op.tfsf.push_back(o->tfsf_attr[i]);
+    for (int i = 0; i < o->n_mat; i++) op.mat.push_back({o->mat_attr[i], {o->mat_eps_mu_sigma[3 * i], o->mat_eps_mu_sigma[3 * i + 1], o->mat_eps_mu_sigma[3 * i + 2]}});
+    if (o->partitioning) op.partitioning.assign(o->partitioning, o->partitioning + mesh->m.ne());
+    if (o->pw.enabled) {
+        // Planewave ctor normalises pol and dir (Function.h:330-339); H polarisation = dir x pol (E-type) / pol x dir gives E (H-type)
+        const dgtd_planewave &w = o->pw;
+        double pn = std::sqrt(w.pol[0] * w.pol[0] + w.pol[1] * w.pol[1] + w.pol[2] * w.pol[2]);
+        double kn = std::sqrt(w.dir[0] * w.dir[0] + w.dir[1] * w.dir[1] + w.dir[2] * w.dir[2]);
+        if (!(pn > 0) || !(kn > 0) || !(w.spread > 0)) throw Error(DGTD_ERR_ARG, "plane wave needs non-zero polarisation, propagation and spread");
+        double p[3], k[3];
+        for (int d = 0; d < 3; d++) { p[d] = w.pol[d] / pn; k[d] = w.dir[d] / kn; }
+        double kxp[3] = {k[1] * p[2] - k[2] * p[1], k[2] * p[0] - k[0] * p[2], k[0] * p[1] - k[1] * p[0]};
+        op.pw.enabled = true; op.pw.spread = w.spread; op.pw.mean1d = w.mean1d; op.pw.freq = w.freq;
+        for (int d = 0; d < 3; d++) {
+            op.pw.dir[d] = k[d];
+            if (w.fieldtype == 0) { op.pw.pe[d] = p[d]; op.pw.ph[d] = kxp[d]; }
+            else { op.pw.ph[d] = p[d]; op.pw.pe[d] = -kxp[d]; }
+        }
+    }
+    return op;
+}
+
+// =====================================================================================================================
+extern "C" {
+
+const char *dgtd_last_error(void) { return g_err.c_str(); }
+const char *dgtd_version(void) { return "dgtd_b200 0.1 (sm_100a, fp64)"; }
+
+int dgtd_mesh_from_arrays(int dim, int nv, const double *verts, int ne, const int *elems, const int *elem_attr, int nbe,
+                          const int *bdr, const int *bdr_attr, dgtd_mesh **out)
+{
+    GUARD_BEGIN
+    if (!out || !verts || !elems || nv <= 0 || ne <= 0 || nbe < 0 || (nbe > 0 && (!bdr || !bdr_attr))) throw Error(DGTD_ERR_ARG, "dgtd_mesh_from_arrays: bad arguments");
+    if (dim < 1 || dim > 3) throw Error(DGTD_ERR_MESH, "mesh dimension must be 1, 2 or 3");
+    auto m = std::make_unique<dgtd_mesh>();
+    m->m.dim = dim;
+    m->m.verts.assign(verts, verts + 3 * (size_t)nv);
+    m->m.elems.assign(elems, elems + (size_t)ne * (dim + 1));
+    if (elem_attr) m->m.elem_attr.assign(elem_attr, elem_attr + ne); else m->m.elem_attr.assign(ne, 1);
+    if (nbe) { m->m.bdr.assign(bdr, bdr + (size_t)nbe * dim); m->m.bdr_attr.assign(bdr_attr, bdr_attr + nbe); }
+    m->m.validate_and_orient();
+    *out = m.release();
+    GUARD_END
+}
+int dgtd_mesh_load(const char *path, dgtd_mesh **out)
+{
+    GUARD_BEGIN
+    if (!path || !out) throw Error(DGTD_ERR_ARG, "dgtd_mesh_load: null argument");
+    auto m = std::make_unique<dgtd_mesh>();
+    m->m = load_mesh(path);
+    *out = m.release();
+    GUARD_END
+}
+int dgtd_mesh_cartesian3d(int nx, int ny, int nz, double sx, double sy, double sz, dgtd_mesh **out)
+{
+    GUARD_BEGIN
+    if (!out) throw Error(DGTD_ERR_ARG, "null out");
+    auto m = std::make_unique<dgtd_mesh>();
+    m->m = cartesian3d(nx, ny, nz, sx, sy, sz);
+    *out = m.release();
+    GUARD_END
+}
+int dgtd_mesh_info(const dgtd_mesh *m, int *dim, int *nv, int *ne, int *nbe)
+{
+    if (!m) return fail(DGTD_ERR_ARG, "null mesh");
+    if (dim) *dim = m->m.dim; if (nv) *nv = m->m.nv(); if (ne) *ne = m->m.ne(); if (nbe) *nbe = m->m.nbe();
+    return DGTD_OK;
+}
+int dgtd_mesh_get_arrays(const dgtd_mesh *m, double *verts, int *elems, int *elem_attr, int *bdr, int *bdr_attr)
+{
+    if (!m) return fail(DGTD_ERR_ARG, "null mesh");
+    auto cp = [](auto *dst, const auto &v) { if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(v[0])); };
+    cp(verts, m->m.verts); cp(elems, m->m.elems); cp(elem_attr, m->m.elem_attr); cp(bdr, m->m.bdr); cp(bdr_attr, m->m.bdr_attr);
+    return DGTD_OK;
+}
+int dgtd_mesh_partition(const dgtd_mesh *m, int nranks, int *partitioning)
+{
+    GUARD_BEGIN
+    if (!m || !partitioning) throw Error(DGTD_ERR_ARG, "null argument");
+    auto p = partition_rcb(m->m, nranks);
+    std::memcpy(partitioning, p.data(), p.size() * sizeof(int));
+    GUARD_END
+}
+void dgtd_mesh_destroy(dgtd_mesh *m) { delete m; }
+
+int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
+{
+    GUARD_BEGIN
+    if (!mesh || !o || !out) throw Error(DGTD_ERR_ARG, "dgtd_create: null argument");
+    Options op = options_from_c(mesh, o);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw Error(DGTD_ERR_CUDA, "no CUDA device: dgtd_b200 has no CPU fallback");
+    if (o->device < 0 || o->device >= ndev) throw Error(DGTD_ERR_CUDA, "CUDA device ordinal out of range");
+    CU(cudaSetDevice(o->device));
+    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, o->device));
+    if (prop.major < 10) throw Error(DGTD_ERR_CUDA, std::string("dgtd_b200 is built for sm_100a only; device is ") + prop.name);
+
+    auto c = std::make_unique<dgtd_ctx>();
+    c->device = o->device; c->rank = op.rank; c->nranks = op.nranks;
+    c->mesh = mesh->m;
+    c->H = build_host_op(mesh->m, op);
+    HostOp &H = c->H;
+    c->Nloc = (long long)H.NEloc * H.Np; c->Nglob = H.NEglob * H.Np;
+    c->ks = select_kernels(H.dim, H.p);
+    if (c->ks.smem > (size_t)prop.sharedMemPerBlockOptin) throw Error(DGTD_ERR_UNSUPPORTED, "order too high for the shared-memory tiling");
+    for (int m = 0; m < 4; m++) CU(cudaFuncSetAttribute((const void *)c->ks.fn[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ks.smem));
+    int occ = 0; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)c->ks.fn[2], c->ks.threads, c->ks.smem));
+    if (occ < 1) throw Error(DGTD_ERR_UNSUPPORTED, "stage kernel does not fit on an SM");
+    {
+        int EB = c->ks.threads / H.Np;
+        long long nbatch = (H.NEloc + EB - 1) / EB;
+        c->grid = (int)std::min<long long>(nbatch, (long long)prop.multiProcessorCount * occ);
+    }
+    CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    // operator tables, transposed for the kernels
+    {
+        const int Np = H.Np, Nfp = H.Nfp, nf = H.nf, dim = H.dim;
+        std::vector<double> Dt((size_t)dim * Np * Np), Lt((size_t)nf * Nfp * Np);
+        for (int x = 0; x < dim; x++) for (int i = 0; i < Np; i++) for (int j = 0; j < Np; j++) Dt[((size_t)x * Np + j) * Np + i] = H.ref.D[((size_t)x * Np + i) * Np + j];
+        for (int f = 0; f < nf; f++) for (int i = 0; i < Np; i++) for (int j = 0; j < Nfp; j++) Lt[((size_t)f * Nfp + j) * Np + i] = H.ref.lift[((size_t)f * Np + i) * Nfp + j];
+        c->D.upload(Dt); c->LIFT.upload(Lt);
+    }
+    c->geo.upload(H.geo); c->finfo.upload(H.finfo); c->ftab.upload(H.ftab, (size_t)256 * H.Nfp);
+    c->tfsf_xyz.upload(H.tfsf_xyz, 3); c->gate_xyz.upload(H.gate_xyz, 3); c->gate.alloc(4);
+    CU(cudaMemset(c->gate.p, 0, 4 * sizeof(double)));
+    c->send_node.upload(H.send_node, 1);
+    const size_t hn = std::max<size_t>(1, (size_t)6 * H.n_halo_faces * H.Nfp);
+    c->halo.alloc(hn); c->sendbuf.alloc(hn); c->scratch.alloc(4);
+    CU(cudaMemset(c->halo.p, 0, hn * sizeof(double)));
+    const size_t n6 = (size_t)6 * c->Nloc;
+    c->x.alloc(n6); c->ya.alloc(n6); c->yb.alloc(n6); c->z.alloc(n6);
+    CU(cudaMemset(c->x.p, 0, n6 * sizeof(double))); CU(cudaMemset(c->ya.p, 0, n6 * sizeof(double)));
+    CU(cudaMemset(c->yb.p, 0, n6 * sizeof(double))); CU(cudaMemset(c->z.p, 0, n6 * sizeof(double)));
+    c->pw_on = H.pw.enabled && H.n_tfsf_faces > 0;
+    if (H.pw.enabled) {
+        c->pw.inv2s2 = 1.0 / (2.0 * H.pw.spread * H.pw.spread); c->pw.mean1d = H.pw.mean1d;
+        c->pw.twopif = 2.0 * M_PI * H.pw.freq;
+        for (int d = 0; d < 3; d++) { c->pw.pe[d] = H.pw.pe[d]; c->pw.ph[d] = H.pw.ph[d]; c->pw.dir[d] = H.pw.dir[d]; }
+    }
+    CU(cudaDeviceSynchronize());
+    *out = c.release();
+    GUARD_END
+}
+void dgtd_destroy(dgtd_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    delete c;
+}
+int dgtd_sizes(const dgtd_ctx *c, long long *n_global, int *np, long long *ne_local, long long *n_local)
+{
+    if (!c) return fail(DGTD_ERR_ARG, "null context");
+    if (n_global) *n_global = c->Nglob; if (np) *np = c->H.Np; if (ne_local) *ne_local = c->H.NEloc; if (n_local) *n_local = c->Nloc;
+    return DGTD_OK;
+}
+int dgtd_local_elements(const dgtd_ctx *c, int *ids)
+{
+    if (!c || !ids) return fail(DGTD_ERR_ARG, "null argument");
+    std::memcpy(ids, c->H.elem_gid.data(), sizeof(int) * c->H.elem_gid.size());
+    return DGTD_OK;
+}
+int dgtd_node_coords(const dgtd_ctx *c, double *xyz)
+{
+    GUARD_BEGIN
+    if (!c || !xyz) throw Error(DGTD_ERR_ARG, "null argument");
+    std::vector<double> v; node_coords(c->mesh, c->H.ref, v);
+    std::memcpy(xyz, v.data(), v.size() * sizeof(double));
+    GUARD_END
+}
+int dgtd_set_stream(dgtd_ctx *c, void *s)
+{
+    if (!c) return fail(DGTD_ERR_ARG, "null context");
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return DGTD_OK;
+}
+int dgtd_set_state(dgtd_ctx *c, const double *h)
+{
+    GUARD_BEGIN
+    if (!c || !h) throw Error(DGTD_ERR_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    scatter_to_device(c, h, c->x.p);
+    GUARD_END
+}
+int dgtd_get_state(dgtd_ctx *c, double *h)
+{
+    GUARD_BEGIN
+    if (!c || !h) throw Error(DGTD_ERR_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    gather_from_device(c, c->x.p, h);
+    GUARD_END
+}
+int dgtd_state_device_ptr(dgtd_ctx *c, double **dev)
+{
+    if (!c || !dev) return fail(DGTD_ERR_ARG, "null argument");
+    *dev = c->x.p;
+    return DGTD_OK;
+}
+int dgtd_mult(dgtd_ctx *c, double t, const double *in, double *out, int on_device)
+{
+    GUARD_BEGIN
+    if (!c || !in || !out) throw Error(DGTD_ERR_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    if (on_device) { mult_device(c, t, in, out); }
+    else {
+        const size_t n6 = (size_t)6 * c->Nloc;
+        if (c->tmp_in.n != n6) { c->tmp_in.alloc(n6); c->tmp_out.alloc(n6); }
+        scatter_to_device(c, in, c->tmp_in.p);
+        mult_device(c, t, c->tmp_in.p, c->tmp_out.p);
+        gather_from_device(c, c->tmp_out.p, out);
+    }
+    GUARD_END
+}
+int dgtd_rk4_step(dgtd_ctx *c, double t, double dt)
+{
+    GUARD_BEGIN
+    if (!c) throw Error(DGTD_ERR_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    rk4_step(c, t, dt);
+    GUARD_END
+}
+int dgtd_rk4_run(dgtd_ctx *c, double t0, double dt, int nsteps)
+{
+    GUARD_BEGIN
+    if (!c || nsteps < 0) throw Error(DGTD_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(c->device));
+    double t = t0;
+    for (int s = 0; s < nsteps; s++) { rk4_step(c, t, dt); t += dt; }
+    GUARD_END
+}
+int dgtd_norm2_local(dgtd_ctx *c, double *sumsq)
+{
+    GUARD_BEGIN
+    if (!c || !sumsq) throw Error(DGTD_ERR_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(c->scratch.p, 0, sizeof(double), c->stream));
+    sumsq_kernel<<<296, 256, 0, c->stream>>>(c->x.p, 6 * c->Nloc, c->scratch.p);
+    c->launches++;
+    CU(cudaMemcpyAsync(sumsq, c->scratch.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    GUARD_END
+}
+int dgtd_sample(dgtd_ctx *c, int npts, const int *elem, const double *shape, double *out6)
+{
+    GUARD_BEGIN
+    if (!c || npts < 0 || (npts && (!elem || !shape || !out6))) throw Error(DGTD_ERR_ARG, "bad argument");
+    if (npts == 0) return DGTD_OK;
+    for (int p = 0; p < npts; p++) if (elem[p] < 0 || elem[p] >= c->H.NEloc) throw Error(DGTD_ERR_ARG, "probe element out of range");
+    CU(cudaSetDevice(c->device));
+    DevBuf<int> de; DevBuf<double> ds, dout;
+    de.alloc(npts); ds.alloc((size_t)npts * c->H.Np); dout.alloc((size_t)npts * 6);
+    CU(cudaMemcpyAsync(de.p, elem, sizeof(int) * npts, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(ds.p, shape, sizeof(double) * npts * c->H.Np, cudaMemcpyHostToDevice, c->stream));
+    sample_kernel<<<(npts + 127) / 128, 128, 0, c->stream>>>(c->x.p, c->Nloc, c->H.Np, npts, de.p, ds.p, dout.p);
+    c->launches++;
+    CU(cudaMemcpyAsync(out6, dout.p, sizeof(double) * npts * 6, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    GUARD_END
+}
+int dgtd_synchronize(dgtd_ctx *c)
+{
+    GUARD_BEGIN
+    if (!c) throw Error(DGTD_ERR_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    GUARD_END
+}
+long long dgtd_launch_count(const dgtd_ctx *c) { return c ? c->launches : 0; }
+
+// Host-only diagnostic: the flat operator tables a rank would upload (no CUDA involved, no compute).
+int dgtd_setup_query(const dgtd_mesh *mesh, const dgtd_options *o, const char *name, void *buf, long long cap_bytes, long long *size_bytes)
+{
+    GUARD_BEGIN
+    if (!mesh || !o || !name || !size_bytes) throw Error(DGTD_ERR_ARG, "null argument");
+    Options op = options_from_c(mesh, o);
+    HostOp H = build_host_op(mesh->m, op);
+    const std::string n = name;
+    const void *src = nullptr; size_t bytes = 0;
+    std::vector<int> dims;
+    std::vector<double> xyz;
+    if (n == "D") { src = H.ref.D.data(); bytes = H.ref.D.size() * 8; }
+    else if (n == "lift") { src = H.ref.lift.data(); bytes = H.ref.lift.size() * 8; }
+    else if (n == "nodes") { src = H.ref.nodes.data(); bytes = H.ref.nodes.size() * 8; }
+    else if (n == "fnodes") { src = H.ref.fnodes.data(); bytes = H.ref.fnodes.size() * 4; }
+    else if (n == "geo") { src = H.geo.data(); bytes = H.geo.size() * 8; }
+    else if (n == "finfo") { src = H.finfo.data(); bytes = H.finfo.size() * 4; }
+    else if (n == "ftab") { src = H.ftab.data(); bytes = H.ftab.size(); }
+    else if (n == "elem_gid") { src = H.elem_gid.data(); bytes = H.elem_gid.size() * 4; }
+    else if (n == "tfsf_xyz") { src = H.tfsf_xyz.data(); bytes = H.tfsf_xyz.size() * 8; }
+    else if (n == "gate_xyz") { src = H.gate_xyz.data(); bytes = H.gate_xyz.size() * 8; }
+    else if (n == "tfsf_side") { src = H.tfsf_side.data(); bytes = H.tfsf_side.size() * 4; }
+    else if (n == "send_node") { src = H.send_node.data(); bytes = H.send_node.size() * 4; }
+    else if (n == "peers") { for (auto &p : H.peers) { dims.push_back(p.rank); dims.push_back(p.nfaces); dims.push_back(p.send_off); } src = dims.data(); bytes = dims.size() * 4; }
+    else if (n == "dims") { dims = {H.dim, H.p, H.Np, H.Nfp, H.nf, H.NEloc, H.ntab, H.n_tfsf_faces, H.n_halo_faces}; src = dims.data(); bytes = dims.size() * 4; }
+    else if (n == "node_coords") { node_coords(mesh->m, H.ref, xyz); src = xyz.data(); bytes = xyz.size() * 8; }
+    else throw Error(DGTD_ERR_ARG, "unknown setup table " + n);
+    *size_bytes = (long long)bytes;
+    if (buf) { if ((long long)bytes > cap_bytes) throw Error(DGTD_ERR_ARG, "buffer too small"); if (bytes) std::memcpy(buf, src, bytes); }
+    GUARD_END
+}
+
+int dgtd_comm_unique_id(void *id128)
+{
+    GUARD_BEGIN
+    if (!id128) throw Error(DGTD_ERR_ARG, "null argument");
+    g_nccl.load();
+    NcclId id; g_nccl.check(g_nccl.GetUniqueId(&id), "ncclGetUniqueId");
+    std::memcpy(id128, &id, 128);
+    GUARD_END
+}
+int dgtd_comm_init(dgtd_ctx *c, const void *id128)
+{
+    GUARD_BEGIN
+    if (!c || !id128) throw Error(DGTD_ERR_ARG, "null argument");
+    if (c->nranks == 1) return DGTD_OK;
+    CU(cudaSetDevice(c->device));
+    g_nccl.load();
+    NcclId id; std::memcpy(&id, id128, 128);
+    g_nccl.check(g_nccl.CommInitRank(&c->comm, c->nranks, id, c->rank), "ncclCommInitRank");
+    GUARD_END
+}
+int dgtd_halo_bytes(const dgtd_ctx *c, long long *bytes)
+{
+    if (!c || !bytes) return fail(DGTD_ERR_ARG, "null argument");
+    *bytes = (long long)6 * c->H.n_halo_faces * c->H.Nfp * 8;
+    return DGTD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+// Host-side data model of the B200 DG-Maxwell operator (C++17, no MFEM, no CUDA).
+// Everything here replaces the SETUP the reference does in
+//   HesthavenEvolution::HesthavenEvolution      src/evolution/HesthavenEvolution.cpp:315-437
+//   Connectivities                               src/evolution/HesthavenEvolutionMethods.cpp:501-534, 721-791
+// (one ParSubMesh + operator assembly PER ELEMENT there; flat arrays built in O(NE) here).
+#pragma once
+#include <array>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace dgtd {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+struct Mesh {
+    int dim = 0;
+    std::vector<double> verts;                 // nv*3
+    std::vector<int> elems, elem_attr;         // ne*(dim+1), ne
+    std::vector<int> bdr, bdr_attr;            // nbe*dim, nbe
+    int nv() const { return (int)(verts.size() / 3); }
+    int ne() const { return (int)elem_attr.size(); }
+    int nbe() const { return (int)bdr_attr.size(); }
+    void validate_and_orient();                // simplex check, swap v0/v1 of inverted elements (mfem/mesh/mesh.cpp:6437-6493)
+};
+Mesh load_mesh(const std::string &path);
+Mesh cartesian3d(int nx, int ny, int nz, double sx, double sy, double sz);
+std::vector<int> partition_rcb(const Mesh &m, int nranks);
+
+// Reference element on the unit simplex with MFEM's L2 Gauss-Lobatto nodes.
+struct RefElem {
+    int dim = 0, p = 0, Np = 0, Nfp = 0, nf = 0;
+    std::vector<double> nodes;     // Np*dim
+    std::vector<int> bary;         // Np*(dim+1): integer barycentric index w.r.t. vertex k
+    std::vector<double> D;         // dim*Np*Np : D[x][i][j] = d l_j / d xi_x (r_i)
+    std::vector<double> Minv;      // Np*Np
+    std::vector<int> fnodes;       // nf*Nfp local node ids on face f (opposite vertex f), ascending
+    std::vector<double> lift;      // nf*Np*Nfp : Minv * (face mass, unit (dim-1)-simplex measure)
+    std::vector<int> node_of;      // lookup: sum_k bary[k+1]*(p+1)^k -> node id (or -1)
+    int lookup(const int *bary_full) const;
+};
+RefElem build_ref_element(int dim, int p);
+std::vector<double> gll01(int p);
+
+struct PlaneWave {
+    bool enabled = false;
+    double spread = 1, mean1d = 0, freq = 0;
+    double pe[3] = {0, 0, 0}, ph[3] = {0, 0, 0}, dir[3] = {0, 0, 1};   // E / H polarisation vectors, unit propagation
+};
+
+struct Options {
+    int order = 3;
+    double alpha = 1.0;
+    std::vector<std::pair<int, int>> bdr;                          // attribute -> DGTD_BC_*
+    std::vector<int> tfsf;
+    std::vector<std::pair<int, std::array<double, 3>>> mat;        // attribute -> eps, mu, sigma
+    PlaneWave pw;
+    bool tfsf_gate = true;
+    int rank = 0, nranks = 1;
+    std::vector<int> partitioning;
+};
+
+// face-info code bits (finfo[e][f].y)
+constexpr int FI_BC_SHIFT = 0, FI_BC_MASK = 3;          // DGTD_BC_*
+constexpr int FI_TFSF_SHIFT = 2, FI_TFSF_MASK = 3;      // 0 none, 1 this side is TF, 2 this side is SF
+constexpr int FI_TAB_SHIFT = 4, FI_TAB_MASK = 0xff;     // row of ftab: neighbour-local node per face node
+constexpr int FI_TIDX_SHIFT = 12;                       // TF/SF face slot (node coordinates)
+constexpr int GEO_STRIDE = 16;                          // doubles per element: Jinv[9], fscale[4], 1/eps, 1/mu, sigma/eps
+
+struct PeerPlan {
+    int rank = -1;
+    int nfaces = 0;
+    int send_off = 0, recv_off = 0;      // in faces, into the packed send list / the halo slots
+};
+
+// Everything a rank uploads to its GPU.
+struct HostOp {
+    int dim = 0, p = 0, Np = 0, Nfp = 0, nf = 0;
+    long long NEglob = 0;
+    int NEloc = 0;
+    RefElem ref;
+    std::vector<int> elem_gid;            // NEloc
+    std::vector<double> geo;              // NEloc*GEO_STRIDE
+    std::vector<int> finfo;               // NEloc*4*2 : {nbr local element | -1 boundary | -2-haloFace, code}
+    std::vector<uint8_t> ftab;            // ntab*Nfp
+    int ntab = 0;
+    // TF/SF
+    std::vector<double> tfsf_xyz;         // nTfsfFaces*Nfp*3 face-node coordinates
+    std::vector<double> gate_xyz;         // V*3 : all nodes of TF/SF-adjacent elements (norm test of `global`)
+    int n_tfsf_faces = 0;
+    std::vector<int> tfsf_side;           // NEloc: 0 none, 1 TF, 2 SF
+    // halo
+    std::vector<PeerPlan> peers;
+    std::vector<int> send_node;           // nSendFaces*Nfp local dof ids, receiver's face-node order
+    int n_halo_faces = 0;
+    // node coordinates of the GLOBAL mesh are produced on demand (node_coords)
+    double alpha = 1.0;
+    PlaneWave pw;
+    bool tfsf_gate = true;
+};
+HostOp build_host_op(const Mesh &m, const Options &o);
+void node_coords(const Mesh &m, const RefElem &ref, std::vector<double> &xyz);   // [NE*Np][3], global numbering
+
+}  // namespace dgtd

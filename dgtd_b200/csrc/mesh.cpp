@@ -1,0 +1,227 @@
+// Simplex meshes on the host: readers for the two formats the reference's cases use
+// (Gmsh 2.2 ASCII as read by mfem::Mesh::LoadFromFile, src/driver/driver.cpp:1176-1183, and "MFEM mesh v1.0"),
+// a Cartesian tetrahedral box generator (config 5: Mesh::MakeCartesian3D(n,n,n,TETRAHEDRON)) and a
+// coordinate-bisection partitioner standing in for METIS (Mesh::GeneratePartitioning, driver.cpp:1269;
+// METIS is not available in the image — same int[NE] contract).
+#include "host.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <fstream>
+#include <map>
+#include <numeric>
+#include <sstream>
+
+namespace dgtd {
+
+static double det_of(const Mesh &m, int e)
+{
+    const int d = m.dim;
+    const int *v = &m.elems[(size_t)e * (d + 1)];
+    const double *x0 = &m.verts[3 * (size_t)v[0]];
+    double J[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int k = 0; k < d; k++) for (int c = 0; c < d; c++) J[c][k] = m.verts[3 * (size_t)v[k + 1] + c] - x0[c];
+    if (d == 1) return J[0][0];
+    if (d == 2) return J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    return J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+           J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+}
+
+void Mesh::validate_and_orient()
+{
+    if (dim < 1 || dim > 3) throw Error(-3, "mesh dimension must be 1, 2 or 3");
+    if (verts.size() % 3) throw Error(-3, "vertex array must hold 3 doubles per vertex");
+    if (elems.size() != (size_t)ne() * (dim + 1) || bdr.size() != (size_t)nbe() * dim) throw Error(-3, "element/boundary array sizes");
+    const int n = nv();
+    for (int v : elems) if (v < 0 || v >= n) throw Error(-3, "element vertex id out of range");
+    for (int v : bdr) if (v < 0 || v >= n) throw Error(-3, "boundary vertex id out of range");
+    for (int e = 0; e < ne(); e++) {
+        double d = det_of(*this, e);
+        if (d == 0.0 || !std::isfinite(d)) throw Error(-3, "degenerate element " + std::to_string(e));
+        if (d < 0.0) {
+            if (dim == 1) throw Error(-3, "inverted segment " + std::to_string(e));
+            std::swap(elems[(size_t)e * (dim + 1)], elems[(size_t)e * (dim + 1) + 1]);
+        }
+    }
+}
+
+static Mesh load_gmsh22(std::istream &in)
+{
+    std::string tok;
+    std::map<long long, int> node_id;          // file node number -> index in xyz
+    std::vector<double> xyz;
+    struct El { int type, phys; std::vector<long long> nodes; };
+    std::vector<El> els;
+    while (in >> tok) {
+        if (tok == "$MeshFormat") {
+            double ver; int ft, ds; in >> ver >> ft >> ds;
+            if (ver < 2.0 || ver >= 3.0 || ft != 0) throw Error(-3, "only Gmsh 2.x ASCII meshes are supported");
+        } else if (tok == "$Nodes") {
+            long long n; in >> n;
+            for (long long i = 0; i < n; i++) {
+                long long id; double x, y, z; in >> id >> x >> y >> z;
+                node_id[id] = (int)(xyz.size() / 3);
+                xyz.push_back(x); xyz.push_back(y); xyz.push_back(z);
+            }
+        } else if (tok == "$Elements") {
+            long long n; in >> n;
+            static const int nn[16] = {0, 2, 3, 4, 4, 8, 6, 5, 3, 6, 9, 10, 27, 18, 14, 1};
+            for (long long i = 0; i < n; i++) {
+                long long id; int type, ntags; in >> id >> type >> ntags;
+                if (type < 1 || type > 15) throw Error(-3, "unsupported Gmsh element type " + std::to_string(type));
+                El e; e.type = type; e.phys = 1;
+                for (int t = 0; t < ntags; t++) { int tag; in >> tag; if (t == 0) e.phys = tag; }
+                e.nodes.resize(nn[type]);
+                for (auto &v : e.nodes) in >> v;
+                els.push_back(std::move(e));
+            }
+        }
+    }
+    if (!in.eof() && in.fail()) throw Error(-3, "malformed Gmsh file");
+    int dim = 0;
+    for (auto &e : els) dim = std::max(dim, e.type == 4 ? 3 : e.type == 2 ? 2 : e.type == 1 ? 1 : 0);
+    if (dim == 0) throw Error(-3, "no simplex elements in Gmsh file");
+    const int etype[4] = {15, 1, 2, 4};
+    Mesh m; m.dim = dim;
+    // vertices: only those used by top-dimensional elements, in order of first use (MFEM renumbers the same way)
+    std::map<long long, int> used;
+    auto vid = [&](long long fileid) {
+        auto it = used.find(fileid);
+        if (it != used.end()) return it->second;
+        auto nt = node_id.find(fileid);
+        if (nt == node_id.end()) throw Error(-3, "element references unknown node");
+        int k = (int)used.size(); used[fileid] = k;
+        for (int c = 0; c < 3; c++) m.verts.push_back(xyz[3 * (size_t)nt->second + c]);
+        return k;
+    };
+    for (auto &e : els) if (e.type == etype[dim]) { for (auto v : e.nodes) m.elems.push_back(vid(v)); m.elem_attr.push_back(e.phys); }
+    for (auto &e : els) if (e.type == etype[dim - 1]) {
+        bool ok = true; for (auto v : e.nodes) ok &= used.count(v) > 0;
+        if (!ok) continue;
+        for (auto v : e.nodes) m.bdr.push_back(used[v]);
+        m.bdr_attr.push_back(e.phys);
+    }
+    return m;
+}
+
+static Mesh load_mfem_v10(std::istream &in)
+{
+    Mesh m; std::string line, tok;
+    auto next = [&](std::string &t) {
+        while (in >> t) { if (t[0] == '#') { std::getline(in, line); continue; } return true; }
+        return false;
+    };
+    while (next(tok)) {
+        if (tok == "dimension") { in >> m.dim; }
+        else if (tok == "elements") {
+            int n; in >> n;
+            for (int i = 0; i < n; i++) {
+                int attr, geom; in >> attr >> geom;
+                int nvx = geom == 1 ? 2 : geom == 2 ? 3 : geom == 4 ? 4 : -1;
+                if (nvx != m.dim + 1) throw Error(-3, "only simplex elements are supported");
+                for (int k = 0; k < nvx; k++) { int v; in >> v; m.elems.push_back(v); }
+                m.elem_attr.push_back(attr);
+            }
+        } else if (tok == "boundary") {
+            int n; in >> n;
+            for (int i = 0; i < n; i++) {
+                int attr, geom; in >> attr >> geom;
+                int nvx = geom == 0 ? 1 : geom == 1 ? 2 : geom == 2 ? 3 : -1;
+                if (nvx != m.dim) throw Error(-3, "boundary element geometry does not match the mesh dimension");
+                for (int k = 0; k < nvx; k++) { int v; in >> v; m.bdr.push_back(v); }
+                m.bdr_attr.push_back(attr);
+            }
+        } else if (tok == "vertices") {
+            int n, sd; in >> n; std::string s; in >> s;
+            if (s == "nodes") throw Error(-4, "curved (nodal) MFEM meshes are not supported");
+            sd = std::stoi(s);
+            for (int i = 0; i < n; i++) { double c[3] = {0, 0, 0}; for (int k = 0; k < sd; k++) in >> c[k]; for (int k = 0; k < 3; k++) m.verts.push_back(c[k]); }
+        }
+    }
+    return m;
+}
+
+Mesh load_mesh(const std::string &path)
+{
+    std::ifstream in(path);
+    if (!in) throw Error(-3, "cannot open mesh file " + path);
+    std::string first; std::getline(in, first);
+    in.seekg(0);
+    Mesh m;
+    if (first.rfind("$MeshFormat", 0) == 0) m = load_gmsh22(in);
+    else if (first.rfind("MFEM mesh v1.0", 0) == 0) { std::getline(in, first); m = load_mfem_v10(in); }
+    else throw Error(-3, "unrecognised mesh format in " + path);
+    m.validate_and_orient();
+    return m;
+}
+
+Mesh cartesian3d(int nx, int ny, int nz, double sx, double sy, double sz)
+{
+    if (nx < 1 || ny < 1 || nz < 1) throw Error(-1, "cartesian3d: cell counts must be positive");
+    if ((long long)nx * ny * nz * 6 > 2000000000LL / 4) throw Error(-1, "cartesian3d: too many elements for 32-bit ids");
+    Mesh m; m.dim = 3;
+    auto vid = [&](int i, int j, int k) { return (k * (ny + 1) + j) * (nx + 1) + i; };
+    for (int k = 0; k <= nz; k++) for (int j = 0; j <= ny; j++) for (int i = 0; i <= nx; i++) {
+        m.verts.push_back(sx * i / nx); m.verts.push_back(sy * j / ny); m.verts.push_back(sz * k / nz);
+    }
+    // Kuhn subdivision: 6 tets around the diagonal (0,0,0)-(1,1,1); conforming across cells
+    static const int perm[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+    for (int k = 0; k < nz; k++) for (int j = 0; j < ny; j++) for (int i = 0; i < nx; i++)
+        for (int t = 0; t < 6; t++) {
+            int c[3] = {0, 0, 0}, v[4];
+            v[0] = vid(i, j, k);
+            for (int s = 0; s < 3; s++) { c[perm[t][s]] = 1; v[s + 1] = vid(i + c[0], j + c[1], k + c[2]); }
+            for (int s = 0; s < 4; s++) m.elems.push_back(v[s]);
+            m.elem_attr.push_back(1);
+        }
+    // boundary triangles: each boundary square is split along the same diagonal as the Kuhn tets
+    auto quad = [&](int a, int b, int c, int d, int attr) {   // a-b-c-d around, diagonal a-c
+        m.bdr.insert(m.bdr.end(), {a, b, c}); m.bdr_attr.push_back(attr);
+        m.bdr.insert(m.bdr.end(), {a, c, d}); m.bdr_attr.push_back(attr);
+    };
+    for (int j = 0; j < ny; j++) for (int i = 0; i < nx; i++) {
+        quad(vid(i, j, 0), vid(i + 1, j, 0), vid(i + 1, j + 1, 0), vid(i, j + 1, 0), 1);
+        quad(vid(i, j, nz), vid(i + 1, j, nz), vid(i + 1, j + 1, nz), vid(i, j + 1, nz), 6);
+    }
+    for (int k = 0; k < nz; k++) for (int i = 0; i < nx; i++) {
+        quad(vid(i, 0, k), vid(i + 1, 0, k), vid(i + 1, 0, k + 1), vid(i, 0, k + 1), 2);
+        quad(vid(i, ny, k), vid(i + 1, ny, k), vid(i + 1, ny, k + 1), vid(i, ny, k + 1), 4);
+    }
+    for (int k = 0; k < nz; k++) for (int j = 0; j < ny; j++) {
+        quad(vid(nx, j, k), vid(nx, j + 1, k), vid(nx, j + 1, k + 1), vid(nx, j, k + 1), 3);
+        quad(vid(0, j, k), vid(0, j + 1, k), vid(0, j + 1, k + 1), vid(0, j, k + 1), 5);
+    }
+    m.validate_and_orient();
+    return m;
+}
+
+static void rcb(const std::vector<double> &bc, std::vector<int> &ids, int lo, int hi, int r0, int nr, std::vector<int> &part)
+{
+    if (nr == 1) { for (int i = lo; i < hi; i++) part[ids[i]] = r0; return; }
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+    for (int i = lo; i < hi; i++) for (int c = 0; c < 3; c++) { double v = bc[3 * (size_t)ids[i] + c]; mn[c] = std::min(mn[c], v); mx[c] = std::max(mx[c], v); }
+    int ax = 0; for (int c = 1; c < 3; c++) if (mx[c] - mn[c] > mx[ax] - mn[ax]) ax = c;
+    int nl = nr / 2;
+    int mid = lo + (int)((long long)(hi - lo) * nl / nr);
+    std::nth_element(ids.begin() + lo, ids.begin() + mid, ids.begin() + hi, [&](int a, int b) {
+        double va = bc[3 * (size_t)a + ax], vb = bc[3 * (size_t)b + ax];
+        return va < vb || (va == vb && a < b);
+    });
+    rcb(bc, ids, lo, mid, r0, nl, part);
+    rcb(bc, ids, mid, hi, r0 + nl, nr - nl, part);
+}
+
+std::vector<int> partition_rcb(const Mesh &m, int nranks)
+{
+    if (nranks < 1) throw Error(-1, "nranks must be positive");
+    const int ne = m.ne(), d = m.dim;
+    std::vector<double> bc(3 * (size_t)ne, 0.0);
+    for (int e = 0; e < ne; e++) for (int k = 0; k <= d; k++) for (int c = 0; c < 3; c++)
+        bc[3 * (size_t)e + c] += m.verts[3 * (size_t)m.elems[(size_t)e * (d + 1) + k] + c] / (d + 1);
+    std::vector<int> ids(ne), part(ne, 0);
+    std::iota(ids.begin(), ids.end(), 0);
+    rcb(bc, ids, 0, ne, 0, nranks, part);
+    return part;
+}
+
+}  // namespace dgtd

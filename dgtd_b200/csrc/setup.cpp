@@ -1,0 +1,309 @@
+// Flat operator data for one rank: geometry factors, face connectivity, boundary / TF-SF codes, halo plan.
+// Replaces (reference file:line)
+//   Connectivities (vmapM/vmapP, mapB/vmapB, TF/SF maps)  src/evolution/HesthavenEvolutionMethods.cpp:501-534, 721-791
+//   normals / fscale / per-element D                       src/evolution/HesthavenEvolution.cpp:150-205
+//   TF/SF side classification (3-D centroid rule)          src/components/SubMesher.cpp:677-771
+//   +-1/2 element mask of the `global` source vector       src/solver/SourcesManager.cpp:158-188
+//   ParMesh ghost layer / send_face_nbr_ldof               external/mfem-geg/fem/pfespace.cpp:1258-1332 (whole elements
+//                                                           there; face traces only here)
+// Face nodes are matched combinatorially through integer barycentric indices, never by assembling
+// two-element flux matrices as the reference does (HesthavenEvolutionMethods.cpp:59-75, 342-370).
+#include "host.hpp"
+#include "../../include/dgtd_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <numeric>
+#include <set>
+
+namespace dgtd {
+namespace {
+
+struct FaceKey {
+    int v[3];
+    int e, f;
+    bool operator<(const FaceKey &o) const { return std::lexicographical_compare(v, v + 3, o.v, o.v + 3); }
+    bool same(const FaceKey &o) const { return v[0] == o.v[0] && v[1] == o.v[1] && v[2] == o.v[2]; }
+};
+
+void elem_geometry(const Mesh &m, int e, double J[3][3], double Jinv[3][3], double &det)
+{
+    const int d = m.dim;
+    const int *v = &m.elems[(size_t)e * (d + 1)];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { J[r][c] = 0; Jinv[r][c] = 0; }
+    for (int k = 0; k < d; k++) for (int c = 0; c < 3; c++) J[c][k] = m.verts[3 * (size_t)v[k + 1] + c] - m.verts[3 * (size_t)v[0] + c];
+    if (d == 1) { det = J[0][0]; Jinv[0][0] = 1.0 / det; }
+    else if (d == 2) {
+        det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+        Jinv[0][0] = J[1][1] / det; Jinv[0][1] = -J[0][1] / det;
+        Jinv[1][0] = -J[1][0] / det; Jinv[1][1] = J[0][0] / det;
+    } else {
+        double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2], c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+        det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+        Jinv[0][0] = c00 / det; Jinv[1][0] = c01 / det; Jinv[2][0] = c02 / det;
+        Jinv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det;
+        Jinv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det;
+        Jinv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det;
+        Jinv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
+        Jinv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
+        Jinv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+    }
+    // Jinv[xi][d] = d xi / d x_d
+}
+
+}  // namespace
+
+void node_coords(const Mesh &m, const RefElem &ref, std::vector<double> &xyz)
+{
+    const int d = m.dim, Np = ref.Np;
+    xyz.assign((size_t)m.ne() * Np * 3, 0.0);
+    for (int e = 0; e < m.ne(); e++) {
+        const int *v = &m.elems[(size_t)e * (d + 1)];
+        for (int n = 0; n < Np; n++) for (int c = 0; c < 3; c++) {
+            double x0 = m.verts[3 * (size_t)v[0] + c], s = x0;
+            for (int k = 0; k < d; k++) s += (m.verts[3 * (size_t)v[k + 1] + c] - x0) * ref.nodes[(size_t)n * d + k];
+            xyz[((size_t)e * Np + n) * 3 + c] = s;
+        }
+    }
+}
+
+HostOp build_host_op(const Mesh &m, const Options &o)
+{
+    HostOp H;
+    const int dim = m.dim, nf = dim + 1, NE = m.ne();
+    if (NE == 0) throw Error(DGTD_ERR_MESH, "empty mesh");
+    if (o.order < 1 || o.order > (dim == 3 ? 5 : 6)) throw Error(DGTD_ERR_UNSUPPORTED, "order out of range for this dimension");
+    if (!(o.alpha >= 0.0 && o.alpha <= 1.0)) throw Error(DGTD_ERR_ARG, "upwind_alpha must lie in [0,1]");
+    if (o.nranks < 1 || o.rank < 0 || o.rank >= o.nranks) throw Error(DGTD_ERR_ARG, "bad rank/nranks");
+    H.ref = build_ref_element(dim, o.order);
+    const RefElem &R = H.ref;
+    const int Np = R.Np, Nfp = R.Nfp;
+    H.dim = dim; H.p = o.order; H.Np = Np; H.Nfp = Nfp; H.nf = nf; H.NEglob = NE;
+    H.alpha = o.alpha; H.pw = o.pw; H.tfsf_gate = o.tfsf_gate;
+    if ((long long)NE * Np > 2000000000LL) throw Error(DGTD_ERR_UNSUPPORTED, "more than 2^31 dofs per field on one rank");
+
+    // ---- global face pairing -------------------------------------------------------------------------------
+    std::vector<FaceKey> keys((size_t)NE * nf);
+    for (int e = 0; e < NE; e++) for (int f = 0; f < nf; f++) {
+        FaceKey &k = keys[(size_t)e * nf + f];
+        k.v[0] = k.v[1] = k.v[2] = -1; int c = 0;
+        for (int q = 0; q < nf; q++) if (q != f) k.v[c++] = m.elems[(size_t)e * nf + q];
+        std::sort(k.v, k.v + dim);
+        k.e = e; k.f = f;
+    }
+    std::vector<FaceKey> sorted = keys;
+    std::sort(sorted.begin(), sorted.end());
+    std::vector<int> nbrE((size_t)NE * nf, -1), nbrF((size_t)NE * nf, -1);
+    for (size_t i = 0; i < sorted.size();) {
+        size_t j = i + 1;
+        while (j < sorted.size() && sorted[j].same(sorted[i])) j++;
+        if (j - i > 2) throw Error(DGTD_ERR_MESH, "non-manifold mesh: a face is shared by more than two elements");
+        if (j - i == 2) {
+            const FaceKey &a = sorted[i], &b = sorted[i + 1];
+            nbrE[(size_t)a.e * nf + a.f] = b.e; nbrF[(size_t)a.e * nf + a.f] = b.f;
+            nbrE[(size_t)b.e * nf + b.f] = a.e; nbrF[(size_t)b.e * nf + b.f] = a.f;
+        }
+        i = j;
+    }
+    // ---- boundary elements -> faces ------------------------------------------------------------------------
+    std::map<int, int> bcOf, matIdx;
+    for (auto &kv : o.bdr) {
+        if (kv.second < DGTD_BC_NONE || kv.second > DGTD_BC_SMA) throw Error(DGTD_ERR_ARG, "unknown boundary condition code");
+        bcOf[kv.first] = kv.second;
+    }
+    std::set<int> tfsfTags(o.tfsf.begin(), o.tfsf.end());
+    std::vector<int> faceBC((size_t)NE * nf, 0);
+    std::vector<int> bdrElemFace(m.nbe(), -1);       // index into sorted[] of the first side
+    for (int b = 0; b < m.nbe(); b++) {
+        FaceKey k; k.v[0] = k.v[1] = k.v[2] = -1;
+        for (int c = 0; c < dim; c++) k.v[c] = m.bdr[(size_t)b * dim + c];
+        std::sort(k.v, k.v + dim);
+        auto it = std::lower_bound(sorted.begin(), sorted.end(), k);
+        if (it == sorted.end() || !it->same(k)) throw Error(DGTD_ERR_MESH, "boundary element " + std::to_string(b) + " is not a face of any element");
+        bdrElemFace[b] = (int)(it - sorted.begin());
+        const int attr = m.bdr_attr[b];
+        const bool interior = nbrE[(size_t)it->e * nf + it->f] >= 0;
+        if (tfsfTags.count(attr)) {
+            if (!interior) throw Error(DGTD_ERR_UNSUPPORTED, "TF/SF tag on a true boundary face");
+            continue;
+        }
+        auto bc = bcOf.find(attr);
+        if (bc == bcOf.end()) continue;
+        if (interior) throw Error(DGTD_ERR_UNSUPPORTED, "interior PEC/PMC/SMA boundaries are not supported yet (attribute " + std::to_string(attr) + ")");
+        faceBC[(size_t)it->e * nf + it->f] = bc->second;
+    }
+    // ---- TF/SF sides (SubMesher.cpp:677-771) ---------------------------------------------------------------
+    std::vector<int> side(NE, 0), faceTF((size_t)NE * nf, 0);
+    if (!tfsfTags.empty() && o.pw.enabled) {
+        if (dim != 3) throw Error(DGTD_ERR_UNSUPPORTED, "TF/SF sources are supported on tetrahedral meshes only");
+        std::set<int> counted; double ctr[3] = {0, 0, 0};
+        for (int b = 0; b < m.nbe(); b++) if (tfsfTags.count(m.bdr_attr[b]))
+            for (int c = 0; c < dim; c++) { int v = m.bdr[(size_t)b * dim + c]; if (counted.insert(v).second) for (int q = 0; q < 3; q++) ctr[q] += m.verts[3 * (size_t)v + q]; }
+        if (!counted.empty()) for (int q = 0; q < 3; q++) ctr[q] /= (double)counted.size();
+        auto dist2 = [&](int e) {
+            double bc3[3] = {0, 0, 0};
+            for (int k = 0; k < nf; k++) for (int q = 0; q < 3; q++) bc3[q] += m.verts[3 * (size_t)m.elems[(size_t)e * nf + k] + q];
+            double s = 0; for (int q = 0; q < 3; q++) { bc3[q] /= nf; s += (bc3[q] - ctr[q]) * (bc3[q] - ctr[q]); }
+            return s;
+        };
+        std::vector<std::pair<int, int>> tfFaces;
+        for (int b = 0; b < m.nbe(); b++) {
+            if (!tfsfTags.count(m.bdr_attr[b])) continue;
+            // Elem1 = the face's first element in MFEM = lower element id
+            const FaceKey &s0 = sorted[bdrElemFace[b]], &s1 = sorted[bdrElemFace[b] + 1];
+            const FaceKey &a = s0.e < s1.e ? s0 : s1, &c = s0.e < s1.e ? s1 : s0;
+            bool e1tf = dist2(a.e) < dist2(c.e);
+            auto mark = [&](int e, bool tf) { if (!tf) side[e] = 2; else if (side[e] == 0) side[e] = 1; };
+            mark(a.e, e1tf); mark(c.e, !e1tf);
+            tfFaces.push_back({a.e, a.f}); tfFaces.push_back({c.e, c.f});
+        }
+        for (auto &ef : tfFaces) faceTF[(size_t)ef.first * nf + ef.second] = side[ef.first];   // the element's mask decides
+    }
+    // ---- neighbour node tables -----------------------------------------------------------------------------
+    std::map<std::vector<uint8_t>, int> tabIdx;
+    auto tabOf = [&](const std::vector<uint8_t> &row) {
+        auto it = tabIdx.find(row);
+        if (it != tabIdx.end()) return it->second;
+        int id = (int)tabIdx.size(); tabIdx[row] = id;
+        H.ftab.insert(H.ftab.end(), row.begin(), row.end());
+        return id;
+    };
+    for (int f = 0; f < nf; f++) {   // rows 0..nf-1: identity (boundary faces read their own trace)
+        std::vector<uint8_t> row(Nfp); for (int j = 0; j < Nfp; j++) row[j] = (uint8_t)R.fnodes[(size_t)f * Nfp + j];
+        tabOf(row);
+    }
+    auto nbrRow = [&](int e, int f, int e2) {
+        // node of e2 coinciding with face node j of (e,f): move the barycentric integers onto e2's vertex order
+        std::vector<uint8_t> row(Nfp);
+        int pos2[4];
+        for (int k = 0; k < nf; k++) {
+            pos2[k] = -1;
+            if (k == f) continue;
+            for (int q = 0; q < nf; q++) if (m.elems[(size_t)e2 * nf + q] == m.elems[(size_t)e * nf + k]) pos2[k] = q;
+            if (pos2[k] < 0) throw Error(DGTD_ERR_MESH, "face vertex mismatch");
+        }
+        for (int j = 0; j < Nfp; j++) {
+            int n = R.fnodes[(size_t)f * Nfp + j], b2[4] = {0, 0, 0, 0};
+            for (int k = 0; k < nf; k++) if (k != f) b2[pos2[k]] = R.bary[(size_t)n * nf + k];
+            int n2 = R.lookup(b2);
+            if (n2 < 0) throw Error(DGTD_ERR_MESH, "face node match failed");
+            row[j] = (uint8_t)n2;
+        }
+        return row;
+    };
+    // ---- partition -----------------------------------------------------------------------------------------
+    std::vector<int> part;
+    if (o.nranks > 1) {
+        part = o.partitioning.empty() ? partition_rcb(m, o.nranks) : o.partitioning;
+        if ((int)part.size() != NE) throw Error(DGTD_ERR_ARG, "partitioning must have one entry per element");
+        for (int r : part) if (r < 0 || r >= o.nranks) throw Error(DGTD_ERR_ARG, "partitioning entry out of range");
+    } else part.assign(NE, 0);
+    std::vector<int> g2l(NE, -1);
+    for (int e = 0; e < NE; e++) if (part[e] == o.rank) { g2l[e] = (int)H.elem_gid.size(); H.elem_gid.push_back(e); }
+    const int NEloc = H.NEloc = (int)H.elem_gid.size();
+    if (NEloc == 0) throw Error(DGTD_ERR_ARG, "rank owns no elements");
+    // shared faces, ordered per peer by (owner-of-lower-rank element id, its face): both sides enumerate identically
+    struct Shared { int peer, keyE, keyF, le, f, ge2, f2; };
+    std::vector<Shared> shared;
+    for (int le = 0; le < NEloc; le++) {
+        int e = H.elem_gid[le];
+        for (int f = 0; f < nf; f++) {
+            int e2 = nbrE[(size_t)e * nf + f];
+            if (e2 < 0 || part[e2] == o.rank) continue;
+            int f2 = nbrF[(size_t)e * nf + f], pr = part[e2];
+            bool mineLow = o.rank < pr;
+            shared.push_back({pr, mineLow ? e : e2, mineLow ? f : f2, le, f, e2, f2});
+        }
+    }
+    std::sort(shared.begin(), shared.end(), [](const Shared &a, const Shared &b) {
+        if (a.peer != b.peer) return a.peer < b.peer;
+        if (a.keyE != b.keyE) return a.keyE < b.keyE;
+        return a.keyF < b.keyF;
+    });
+    H.n_halo_faces = (int)shared.size();
+    std::map<std::pair<int, int>, int> haloSlot;   // (le, f) -> slot
+    for (size_t s = 0; s < shared.size(); s++) {
+        const Shared &sh = shared[s];
+        if (H.peers.empty() || H.peers.back().rank != sh.peer) { PeerPlan pp; pp.rank = sh.peer; pp.send_off = pp.recv_off = (int)s; H.peers.push_back(pp); }
+        H.peers.back().nfaces++;
+        haloSlot[{sh.le, sh.f}] = (int)s;
+        // what I send for this face: my nodes in the RECEIVER's face-node order
+        int e = H.elem_gid[sh.le];
+        auto row = nbrRow(sh.ge2, sh.f2, e);          // for receiver's face node j -> my local node
+        for (int j = 0; j < Nfp; j++) H.send_node.push_back(sh.le * Np + row[j]);
+    }
+    // ---- per-element records -------------------------------------------------------------------------------
+    std::map<int, std::array<double, 3>> mats;
+    for (auto &kv : o.mat) {
+        if (!(kv.second[0] > 0 && kv.second[1] > 0) || kv.second[2] < 0) throw Error(DGTD_ERR_ARG, "material needs eps > 0, mu > 0, sigma >= 0");
+        mats[kv.first] = kv.second;
+    }
+    H.geo.assign((size_t)NEloc * GEO_STRIDE, 0.0);
+    H.finfo.assign((size_t)NEloc * 4 * 2, 0);
+    H.tfsf_side.assign(NEloc, 0);
+    std::vector<double> xyzTF;
+    for (int le = 0; le < NEloc; le++) {
+        const int e = H.elem_gid[le];
+        double J[3][3], Ji[3][3], det;
+        elem_geometry(m, e, J, Ji, det);
+        if (!(det > 0)) throw Error(DGTD_ERR_MESH, "element with non-positive Jacobian");
+        double *g = &H.geo[(size_t)le * GEO_STRIDE];
+        for (int x = 0; x < 3; x++) for (int d = 0; d < 3; d++) g[3 * x + d] = Ji[x][d];
+        for (int f = 0; f < nf; f++) {   // |grad lambda_f| = |J_f| / |J_e|
+            double gl[3];
+            for (int d = 0; d < 3; d++) {
+                if (f == 0) { gl[d] = 0; for (int x = 0; x < dim; x++) gl[d] -= Ji[x][d]; }
+                else gl[d] = Ji[f - 1][d];
+            }
+            g[9 + f] = std::sqrt(gl[0] * gl[0] + gl[1] * gl[1] + gl[2] * gl[2]);
+        }
+        std::array<double, 3> mt{1.0, 1.0, 0.0};
+        auto mi = mats.find(m.elem_attr[e]); if (mi != mats.end()) mt = mi->second;
+        g[13] = 1.0 / mt[0]; g[14] = 1.0 / mt[1]; g[15] = mt[2] / mt[0];
+        H.tfsf_side[le] = side[e];
+        for (int f = 0; f < nf; f++) {
+            int *fi = &H.finfo[((size_t)le * 4 + f) * 2];
+            int e2 = nbrE[(size_t)e * nf + f], code = 0, tab = f, nb = -1;
+            if (e2 >= 0) {
+                tab = tabOf(nbrRow(e, f, e2));
+                if (part[e2] == o.rank) nb = g2l[e2];
+                else nb = -2 - haloSlot[{le, f}];
+            } else code |= (faceBC[(size_t)e * nf + f] & FI_BC_MASK) << FI_BC_SHIFT;
+            if (tab > FI_TAB_MASK) throw Error(DGTD_ERR_UNSUPPORTED, "too many distinct face orientations");
+            code |= tab << FI_TAB_SHIFT;
+            int tf = faceTF[(size_t)e * nf + f];
+            if (tf) {
+                code |= (tf & FI_TFSF_MASK) << FI_TFSF_SHIFT;
+                code |= H.n_tfsf_faces << FI_TIDX_SHIFT;
+                if (H.n_tfsf_faces >= (1 << (31 - FI_TIDX_SHIFT))) throw Error(DGTD_ERR_UNSUPPORTED, "too many TF/SF faces");
+                for (int j = 0; j < Nfp; j++) {
+                    int n = R.fnodes[(size_t)f * Nfp + j];
+                    for (int c = 0; c < 3; c++) {
+                        double x0 = m.verts[3 * (size_t)m.elems[(size_t)e * nf] + c], s = x0;
+                        for (int k = 0; k < dim; k++) s += J[c][k] * R.nodes[(size_t)n * dim + k];
+                        H.tfsf_xyz.push_back(s);
+                    }
+                }
+                H.n_tfsf_faces++;
+            }
+            fi[0] = nb; fi[1] = code;
+        }
+    }
+    // gate: every node of EVERY TF/SF-adjacent element of the global mesh (SourcesManager.cpp:136-156); the norm test
+    // is a function of time only, so each rank evaluates the global sum itself instead of all-reducing it
+    for (int e = 0; e < NE; e++) {
+        if (!side[e]) continue;
+        double J[3][3], Ji[3][3], det;
+        elem_geometry(m, e, J, Ji, det);
+        for (int n = 0; n < Np; n++) for (int c = 0; c < 3; c++) {
+            double x0 = m.verts[3 * (size_t)m.elems[(size_t)e * nf] + c], s = x0;
+            for (int k = 0; k < dim; k++) s += J[c][k] * R.nodes[(size_t)n * dim + k];
+            H.gate_xyz.push_back(s);
+        }
+    }
+    H.ntab = (int)tabIdx.size();
+    return H;
+}
+
+}  // namespace dgtd

@@ -1,0 +1,153 @@
+/* dgtd_b200 — C ABI of the B200-native DG-Maxwell evolution hot path.
+ *
+ * Drop-in boundary for OpenSEMBA/dgtd's evolution operators.  The reference has
+ * no FFI: its seam is the C++ virtual interface
+ *     mfem::TimeDependentOperator::Mult(const Vector&, Vector&) const   (external/mfem-geg/linalg/operator.hpp:89, 391-394)
+ * implemented by
+ *     maxwell::GlobalEvolution      src/evolution/GlobalEvolution.h:19-22, GlobalEvolution.cpp:628-1088
+ *     maxwell::HesthavenEvolution   src/evolution/HesthavenEvolution.h:20-21, HesthavenEvolution.cpp:450-542
+ * and driven by mfem::RK4Solver::Step (external/mfem-geg/linalg/ode.cpp:109-136) from
+ * maxwell::Solver::step (src/solver/Solver.cpp:535-551).  The two thin C++ shells in
+ * dgtd_b200/mfem_shell/ (B200Evolution, B200RK4Solver) are the only callers a
+ * maintainer adds on the reference side; they bind exactly the entry points below
+ * (see INTEGRATION.md).
+ *
+ * Conventions: every function returns DGTD_OK (0) or a negative error code and never
+ * throws; dgtd_last_error() gives the message of the last failure on the calling
+ * thread (the shells turn it into std::runtime_error like the reference does,
+ * src/solver/Solver.cpp:37,74).  All pointers are caller-owned unless returned by a
+ * *_create / *_load function.  One host thread per context; calls on a context are
+ * serialised (the reference's Mult is not re-entrant either, GlobalEvolution.h:82-90).
+ * State layout is the reference's (src/evolution/Fields.h:45-65): 6 blocks
+ * [Ex,Ey,Ez,Hx,Hy,Hz] of N doubles, dof = element*Np + local node, MFEM L2
+ * Gauss-Lobatto simplex node order (external/mfem-geg/fem/fe/fe_l2.cpp:716-722).
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef DGTD_B200_H
+#define DGTD_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGTD_OK               0
+#define DGTD_ERR_ARG         -1   /* invalid argument / null pointer / size mismatch            */
+#define DGTD_ERR_CUDA        -2   /* CUDA runtime failure or no usable device                   */
+#define DGTD_ERR_MESH        -3   /* unreadable / inconsistent / non-simplex / inverted mesh    */
+#define DGTD_ERR_UNSUPPORTED -4   /* order/dimension/feature outside what the kernels cover     */
+#define DGTD_ERR_COMM        -5   /* NCCL / halo exchange failure                               */
+
+/* boundary conditions — BdrCond in src/components/Types.h:48-56 */
+#define DGTD_BC_NONE 0
+#define DGTD_BC_PEC  1
+#define DGTD_BC_PMC  2
+#define DGTD_BC_SMA  3
+
+typedef struct dgtd_mesh dgtd_mesh;   /* host-side simplex mesh (segments / triangles / tetrahedra) */
+typedef struct dgtd_ctx  dgtd_ctx;    /* one per GPU (rank): owns all device memory, streams, comms  */
+
+/* Gaussian / modulated-Gaussian plane wave — maxwell::Planewave, src/math/Function.h:328-409,
+ * built by driver.cpp:483-519.  g(u) = exp(-(u-mean1d)^2/(2 spread^2)) [* cos(2 pi freq (u-mean1d))],
+ * u = dir.x - t (c = 1).  pol/dir are normalised by the library as the reference ctor does. */
+typedef struct dgtd_planewave {
+    int    enabled;
+    double spread, mean1d, freq;   /* freq == 0: plain Gaussian */
+    double pol[3], dir[3];
+    int    fieldtype;              /* 0: pol is the E polarisation, 1: pol is H */
+} dgtd_planewave;
+
+/* What maxwell::Model + EvolutionOptions + Sources give the reference ctor
+ * (src/evolution/GlobalEvolution.cpp:32-364; EvolutionOptions.h:13-20). */
+typedef struct dgtd_options {
+    int    order;                       /* 1..6 (tets: 1..5)                                       */
+    double alpha;                       /* upwind_alpha in [0,1]                                   */
+    int    n_bdr;                       /* boundary attribute -> condition                         */
+    const int *bdr_attr, *bdr_cond;
+    int    n_tfsf;                      /* attributes of interior TF/SF faces (3-D)                */
+    const int *tfsf_attr;
+    int    n_mat;                       /* element attribute -> (eps, mu, sigma); default vacuum   */
+    const int *mat_attr;
+    const double *mat_eps_mu_sigma;     /* 3 doubles per entry                                     */
+    dgtd_planewave pw;
+    int    tfsf_gate;                   /* 1: skip injection when ||s|| < 1e-8 like `global`
+                                           (GlobalEvolution.cpp:584-598); 0: never skip (`hesthaven`) */
+    int    device;                      /* CUDA device ordinal                                     */
+    int    rank, nranks;                /* partition of the mesh this context owns                 */
+    const int *partitioning;            /* [NE] element -> rank, or NULL = built-in partitioner
+                                           (same contract as Mesh::GeneratePartitioning, driver.cpp:1269) */
+} dgtd_options;
+
+/* ---- mesh (host) ---------------------------------------------------------------------------- */
+/* verts: nv*3 doubles (unused coordinates 0); elems: ne*(dim+1) vertex ids in the host code's
+ * element-local order (mfem::Mesh::GetElementVertices); bdr: nbe*dim vertex ids.                  */
+int  dgtd_mesh_from_arrays(int dim, int nv, const double *verts, int ne, const int *elems,
+                           const int *elem_attr, int nbe, const int *bdr, const int *bdr_attr,
+                           dgtd_mesh **out);
+/* Gmsh 2.2 ASCII (.msh, attribute = physical tag as MFEM reads it) or "MFEM mesh v1.0" (.mesh).   */
+int  dgtd_mesh_load(const char *path, dgtd_mesh **out);
+/* nx*ny*nz cubes of 6 tetrahedra on [0,sx]x[0,sy]x[0,sz]; boundary attributes 1..6 =
+ * bottom(z=0), front(y=0), right(x=sx), back(y=sy), left(x=0), top(z=sz) (MFEM's MakeCartesian3D). */
+int  dgtd_mesh_cartesian3d(int nx, int ny, int nz, double sx, double sy, double sz, dgtd_mesh **out);
+int  dgtd_mesh_info(const dgtd_mesh *, int *dim, int *nv, int *ne, int *nbe);
+/* copies out what dgtd_mesh_from_arrays takes in (any pointer may be NULL)                        */
+int  dgtd_mesh_get_arrays(const dgtd_mesh *, double *verts, int *elems, int *elem_attr, int *bdr, int *bdr_attr);
+/* element -> rank by recursive coordinate bisection of element barycentres (METIS is not in the image) */
+int  dgtd_mesh_partition(const dgtd_mesh *, int nranks, int *partitioning);
+void dgtd_mesh_destroy(dgtd_mesh *);
+
+/* ---- context = the evolution operator ----------------------------------------------------------- */
+/* Replaces GlobalEvolution::GlobalEvolution / HesthavenEvolution::HesthavenEvolution.             */
+int  dgtd_create(const dgtd_mesh *, const dgtd_options *, dgtd_ctx **out);
+void dgtd_destroy(dgtd_ctx *);
+/* sizes: global scalar dofs N (state = 6N), dofs per element, owned elements/dofs of this rank   */
+int  dgtd_sizes(const dgtd_ctx *, long long *n_global, int *np, long long *ne_local, long long *n_local);
+/* global element id of every local element, in local order [ne_local]                            */
+int  dgtd_local_elements(const dgtd_ctx *, int *elem_ids);
+/* physical node coordinates, global numbering, [N][3] (what GridFunction::ProjectCoefficient
+ * evaluates initial fields at, SourcesManager.cpp:28-32)                                         */
+int  dgtd_node_coords(const dgtd_ctx *, double *xyz);
+/* use a caller-provided cudaStream_t for all work (NULL: the context's own stream)                */
+int  dgtd_set_stream(dgtd_ctx *, void *cuda_stream);
+
+/* state: host vectors are GLOBAL [6N] in the reference layout; a rank reads/writes only the
+ * entries of the elements it owns (other entries of `host_6N` are left untouched on get).         */
+int  dgtd_set_state(dgtd_ctx *, const double *host_6N);
+int  dgtd_get_state(dgtd_ctx *, double *host_6N);
+/* device-resident state of this rank: [6][n_local] doubles (local element order)                  */
+int  dgtd_state_device_ptr(dgtd_ctx *, double **dev);
+
+/* TimeDependentOperator::Mult at time t (SetTime + Mult).  Host pointers: global [6N] vectors,
+ * copied in/out (each rank fills its owned entries of out).  Device pointers (on_device=1):
+ * local [6][n_local] vectors, no copies.                                                          */
+int  dgtd_mult(dgtd_ctx *, double t, const double *in, double *out, int on_device);
+/* mfem::RK4Solver::Step on the resident state, fused: 4 launches, k never stored
+ * (ode.cpp:109-136 semantics incl. the SetTime sequence t, t+dt/2, t+dt/2, t+dt).                 */
+int  dgtd_rk4_step(dgtd_ctx *, double t, double dt);
+/* nsteps of the above from t0 (Solver::run loop body, Solver.cpp:483-533, without probes)         */
+int  dgtd_rk4_run(dgtd_ctx *, double t0, double dt, int nsteps);
+/* ||state||_2 over all ranks' owned dofs of THIS rank (caller reduces) — Fields::getNorml2        */
+int  dgtd_norm2_local(dgtd_ctx *, double *sumsq);
+/* point probes: field values at npts (local element, Np shape weights) -> out[npts][6]            */
+int  dgtd_sample(dgtd_ctx *, int npts, const int *local_elem, const double *shape, double *out6);
+int  dgtd_synchronize(dgtd_ctx *);
+/* number of kernel launches issued by this context so far (bench.py's gpu_launches)               */
+long long dgtd_launch_count(const dgtd_ctx *);
+
+/* ---- multi-GPU halo exchange (one context per rank/GPU, NCCL over NVLink) ----------------------- */
+int  dgtd_comm_unique_id(void *id128);                    /* rank 0: ncclGetUniqueId              */
+int  dgtd_comm_init(dgtd_ctx *, const void *id128);       /* all ranks: ncclCommInitRank          */
+/* bytes this rank sends per RHS evaluation (6 * Nfp * shared faces * 8)                          */
+int  dgtd_halo_bytes(const dgtd_ctx *, long long *bytes);
+
+/* Host-only diagnostic (no CUDA, no compute): copies one of the flat tables a rank would upload — "dims", "D", "lift",
+ * "nodes", "fnodes", "geo", "finfo", "ftab", "elem_gid", "tfsf_xyz", "gate_xyz", "tfsf_side", "send_node", "peers",
+ * "node_coords" — so that tests can check the setup against the oracle without a GPU.                            */
+int  dgtd_setup_query(const dgtd_mesh *, const dgtd_options *, const char *name, void *buf, long long cap_bytes, long long *size_bytes);
+
+const char *dgtd_last_error(void);
+const char *dgtd_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGTD_B200_H */
