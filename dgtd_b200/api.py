@@ -221,6 +221,18 @@ class Evolution:
         _ck(lib.dgtd_get_state(self._h, _dp(out)))
         return out
 
+    def set_state_local(self, x):
+        x = np.ascontiguousarray(x, np.float64)
+        if x.size != 6 * self.n_local:
+            raise DgtdError(-1, "set_state_local: wrong size")
+        _ck(lib.dgtd_set_state_local(self._h, _dp(x)))
+
+    def get_state_local(self, out=None):
+        if out is None:
+            out = np.zeros(6 * self.n_local)
+        _ck(lib.dgtd_get_state_local(self._h, _dp(out)))
+        return out
+
     def Step(self, t, dt):
         _ck(lib.dgtd_rk4_step(self._h, C.c_double(t), C.c_double(dt)))
         return t + dt

@@ -433,6 +433,24 @@ int dgtd_get_state(dgtd_ctx *c, double *h)
     gather_from_device(c, c->x.p, h);
     GUARD_END
 }
+int dgtd_set_state_local(dgtd_ctx *c, const double *h)
+{
+    GUARD_BEGIN
+    if (!c || !h) throw Error(DGTD_ERR_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(c->x.p, h, sizeof(double) * 6 * c->Nloc, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    GUARD_END
+}
+int dgtd_get_state_local(dgtd_ctx *c, double *h)
+{
+    GUARD_BEGIN
+    if (!c || !h) throw Error(DGTD_ERR_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(h, c->x.p, sizeof(double) * 6 * c->Nloc, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    GUARD_END
+}
 int dgtd_state_device_ptr(dgtd_ctx *c, double **dev)
 {
     if (!c || !dev) return fail(DGTD_ERR_ARG, "null argument");

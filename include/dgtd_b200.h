@@ -113,6 +113,9 @@ int  dgtd_set_stream(dgtd_ctx *, void *cuda_stream);
  * entries of the elements it owns (other entries of `host_6N` are left untouched on get).         */
 int  dgtd_set_state(dgtd_ctx *, const double *host_6N);
 int  dgtd_get_state(dgtd_ctx *, double *host_6N);
+/* the same with LOCAL host vectors [6][n_local] in this rank's element order (dgtd_local_elements)  */
+int  dgtd_set_state_local(dgtd_ctx *, const double *host_6nlocal);
+int  dgtd_get_state_local(dgtd_ctx *, double *host_6nlocal);
 /* device-resident state of this rank: [6][n_local] doubles (local element order)                  */
 int  dgtd_state_device_ptr(dgtd_ctx *, double **dev);
 
