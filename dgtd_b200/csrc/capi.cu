@@ -7,9 +7,11 @@
 #include "../../include/dgtd_b200.h"
 #include "host.hpp"
 #include "kernels.cuh"
+#include "kernels_mma.cuh"
 
 #include <dlfcn.h>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -105,8 +107,34 @@ static KernelSet select_kernels(int dim, int p)
     throw Error(DGTD_ERR_UNSUPPORTED, "no kernel for this dimension/order");
 }
 
+typedef void (*MmaFn)(const MmaArgs);
+struct MmaSet { MmaFn fn[4]; int threads; size_t smem; };
+template <int P> static MmaSet mset()
+{
+    using B = Blk<P, 1>;
+    return {{stage_mma_kernel<P, 1, 0>, stage_mma_kernel<P, 1, 1>, stage_mma_kernel<P, 1, 2>, stage_mma_kernel<P, 1, 3>}, B::T, B::smem_bytes};
+}
+// the DMMA kernel covers tetrahedra of order 1..4 (order 5 does not fit the shared-memory tiling: generic kernel)
+static bool select_mma(int dim, int p, MmaSet &ms)
+{
+    if (dim != 3) return false;
+    switch (p) {
+        case 1: ms = mset<1>(); return true; case 2: ms = mset<2>(); return true;
+        case 3: ms = mset<3>(); return true; case 4: ms = mset<4>(); return true;
+    }
+    return false;
+}
+
 struct dgtd_ctx {
     HostOp H;
+    BlockedPlan BP;
+    bool blocked = false;            // state lives in the blocked layout and the DMMA stage kernel runs
+    bool identity = true;            // local element order == global order (single rank, no reordering)
+    long long Nalloc = 0;            // scalar dofs allocated per component (padded to whole batches when blocked)
+    MmaSet ms{};
+    DevBuf<double> bgeo, bafrag, stage_ref;
+    DevBuf<int> bfinfo, btdesc, btcount;
+    DevBuf<long long> bsend_off;
     Mesh mesh;                       // kept for node_coords
     int device = 0;
     int rank = 0, nranks = 1;
@@ -145,6 +173,18 @@ static void exchange(dgtd_ctx *c, const double *y)
     if (!c->comm) throw Error(DGTD_ERR_COMM, "multi-rank context used before dgtd_comm_init");
     const int Nfp = c->H.Nfp;
     const int ns = c->H.n_halo_faces * Nfp;
+    if (c->blocked) {   // node records [face][node][6], one contiguous message per peer
+        pack_blocked_kernel<<<std::min(1024, (3 * ns + 255) / 256), 256, 0, c->stream>>>(y, c->bsend_off.p, ns, c->sendbuf.p);
+        c->launches++;
+        g_nccl.check(g_nccl.GroupStart(), "ncclGroupStart");
+        for (auto &pp : c->H.peers) {
+            const size_t off = (size_t)pp.send_off * Nfp * 6, cnt = (size_t)pp.nfaces * Nfp * 6;
+            g_nccl.check(g_nccl.Send(c->sendbuf.p + off, cnt, NCCL_FLOAT64, pp.rank, c->comm, c->stream), "ncclSend");
+            g_nccl.check(g_nccl.Recv(c->halo.p + off, cnt, NCCL_FLOAT64, pp.rank, c->comm, c->stream), "ncclRecv");
+        }
+        g_nccl.check(g_nccl.GroupEnd(), "ncclGroupEnd");
+        return;
+    }
     pack_kernel<<<std::min(1024, (ns + 255) / 256), 256, 0, c->stream>>>(y, c->Nloc, c->send_node.p, ns, c->sendbuf.p, ns);
     c->launches++;
     g_nccl.check(g_nccl.GroupStart(), "ncclGroupStart");
@@ -168,7 +208,16 @@ static void launch_gate(dgtd_ctx *c, const double *ts, int nt)
 static void launch_stage(dgtd_ctx *c, int mode, StageArgs &A)
 {
     exchange(c, A.yin);
-    c->ks.fn[mode]<<<c->grid, c->ks.threads, c->ks.smem, c->stream>>>(A);
+    if (c->blocked) {
+        MmaArgs M;
+        M.afrag = c->bafrag.p; M.geo = c->bgeo.p; M.finfo = reinterpret_cast<const int2 *>(c->bfinfo.p);
+        M.tdesc = reinterpret_cast<const int2 *>(c->btdesc.p); M.tcount = c->btcount.p; M.ftab = c->ftab.p; M.ntab = c->H.ntab;
+        M.tfsf_xyz = A.tfsf_xyz; M.gate = A.gate; M.halo = A.halo; M.nbatch = c->BP.nbatch; M.alpha = A.alpha; M.pw = A.pw; M.pw_on = A.pw_on;
+        M.yin = A.yin; M.x = A.x; M.z = A.z; M.yout = A.yout; M.a = A.a; M.b = A.b; M.t = A.t;
+        c->ms.fn[mode]<<<c->grid, c->ms.threads, c->ms.smem, c->stream>>>(M);
+    } else {
+        c->ks.fn[mode]<<<c->grid, c->ks.threads, c->ks.smem, c->stream>>>(A);
+    }
     c->launches++;
     CU(cudaGetLastError());
 }
@@ -202,33 +251,50 @@ static void mult_device(dgtd_ctx *c, double t, const double *in, double *out)
     launch_stage(c, MODE_MULT, A);
 }
 
-// global [6N] host vector <-> local [6][Nloc] device vector
+// local reference-layout host vector [6][Nloc] <-> device state (reference layout, or blocked through a staging buffer)
+static void upload_local(dgtd_ctx *c, const double *hloc, double *dev)
+{
+    const long long Nl = c->Nloc;
+    if (!c->blocked) {
+        CU(cudaMemcpyAsync(dev, hloc, sizeof(double) * 6 * Nl, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        if (c->stage_ref.n != (size_t)6 * Nl) c->stage_ref.alloc((size_t)6 * Nl);
+        CU(cudaMemcpyAsync(c->stage_ref.p, hloc, sizeof(double) * 6 * Nl, cudaMemcpyHostToDevice, c->stream));
+        to_blocked_kernel<<<1184, 256, 0, c->stream>>>(c->stage_ref.p, Nl, c->H.Np, c->H.NEloc, c->BP.NEpad, dev);
+        c->launches++;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+}
+static void download_local(dgtd_ctx *c, const double *dev, double *hloc)
+{
+    const long long Nl = c->Nloc;
+    if (!c->blocked) {
+        CU(cudaMemcpyAsync(hloc, dev, sizeof(double) * 6 * Nl, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        if (c->stage_ref.n != (size_t)6 * Nl) c->stage_ref.alloc((size_t)6 * Nl);
+        from_blocked_kernel<<<1184, 256, 0, c->stream>>>(dev, Nl, c->H.Np, c->H.NEloc, c->stage_ref.p);
+        c->launches++;
+        CU(cudaMemcpyAsync(hloc, c->stage_ref.p, sizeof(double) * 6 * Nl, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+}
+// global [6N] host vector <-> device state of this rank
 static void scatter_to_device(dgtd_ctx *c, const double *host, double *dev)
 {
     const int Np = c->H.Np; const long long Ng = c->Nglob, Nl = c->Nloc;
-    if (c->nranks == 1) {   // identity element order
-        CU(cudaMemcpyAsync(dev, host, sizeof(double) * 6 * Nl, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        return;
-    }
+    if (c->identity) { upload_local(c, host, dev); return; }
     c->hostbuf.resize((size_t)6 * Nl);
     for (int comp = 0; comp < 6; comp++)
         for (int le = 0; le < c->H.NEloc; le++)
             std::memcpy(&c->hostbuf[(size_t)comp * Nl + (size_t)le * Np], host + (size_t)comp * Ng + (size_t)c->H.elem_gid[le] * Np, sizeof(double) * Np);
-    CU(cudaMemcpyAsync(dev, c->hostbuf.data(), sizeof(double) * 6 * Nl, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    upload_local(c, c->hostbuf.data(), dev);
 }
 static void gather_from_device(dgtd_ctx *c, const double *dev, double *host)
 {
     const int Np = c->H.Np; const long long Ng = c->Nglob, Nl = c->Nloc;
-    if (c->nranks == 1) {
-        CU(cudaMemcpyAsync(host, dev, sizeof(double) * 6 * Nl, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        return;
-    }
+    if (c->identity) { download_local(c, dev, host); return; }
     c->hostbuf.resize((size_t)6 * Nl);
-    CU(cudaMemcpyAsync(c->hostbuf.data(), dev, sizeof(double) * 6 * Nl, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    download_local(c, dev, c->hostbuf.data());
     for (int comp = 0; comp < 6; comp++)
         for (int le = 0; le < c->H.NEloc; le++)
             std::memcpy(host + (size_t)comp * Ng + (size_t)c->H.elem_gid[le] * Np, &c->hostbuf[(size_t)comp * Nl + (size_t)le * Np], sizeof(double) * Np);
@@ -344,12 +410,27 @@ int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
     c->H = build_host_op(mesh->m, op);
     HostOp &H = c->H;
     c->Nloc = (long long)H.NEloc * H.Np; c->Nglob = H.NEglob * H.Np;
-    c->ks = select_kernels(H.dim, H.p);
-    if (c->ks.smem > (size_t)prop.sharedMemPerBlockOptin) throw Error(DGTD_ERR_UNSUPPORTED, "order too high for the shared-memory tiling");
-    for (int m = 0; m < 4; m++) CU(cudaFuncSetAttribute((const void *)c->ks.fn[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ks.smem));
-    int occ = 0; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)c->ks.fn[2], c->ks.threads, c->ks.smem));
-    if (occ < 1) throw Error(DGTD_ERR_UNSUPPORTED, "stage kernel does not fit on an SM");
-    {
+    c->identity = c->nranks == 1;
+    for (int le = 0; le < H.NEloc && c->identity; le++) c->identity = H.elem_gid[le] == le;
+    const char *force_v1 = std::getenv("DGTD_B200_GENERIC_KERNEL");   // diagnostics: run the generic (non-DMMA) kernel
+    c->blocked = !(force_v1 && force_v1[0] == '1') && H.ntab <= 128 && select_mma(H.dim, H.p, c->ms);
+    if (c->blocked && c->ms.smem > (size_t)prop.sharedMemPerBlockOptin) c->blocked = false;
+    if (c->blocked) {
+        c->BP = build_blocked_plan(H, 1);
+        c->Nalloc = (long long)c->BP.NEpad * H.Np;
+        for (int m = 0; m < 4; m++) CU(cudaFuncSetAttribute((const void *)c->ms.fn[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ms.smem));
+        int occ = 0; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)c->ms.fn[2], c->ms.threads, c->ms.smem));
+        if (occ < 1) throw Error(DGTD_ERR_UNSUPPORTED, "DMMA stage kernel does not fit on an SM");
+        c->grid = (int)std::min<long long>(c->BP.nbatch, (long long)prop.multiProcessorCount * occ);
+        c->bgeo.upload(c->BP.geo); c->bafrag.upload(c->BP.afrag); c->bfinfo.upload(c->BP.finfo);
+        c->btdesc.upload(c->BP.tdesc); c->btcount.upload(c->BP.tcount); c->bsend_off.upload(c->BP.send_off, 1);
+    } else {
+        c->Nalloc = c->Nloc;
+        c->ks = select_kernels(H.dim, H.p);
+        if (c->ks.smem > (size_t)prop.sharedMemPerBlockOptin) throw Error(DGTD_ERR_UNSUPPORTED, "order too high for the shared-memory tiling");
+        for (int m = 0; m < 4; m++) CU(cudaFuncSetAttribute((const void *)c->ks.fn[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ks.smem));
+        int occ = 0; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)c->ks.fn[2], c->ks.threads, c->ks.smem));
+        if (occ < 1) throw Error(DGTD_ERR_UNSUPPORTED, "stage kernel does not fit on an SM");
         int EB = c->ks.threads / H.Np;
         long long nbatch = (H.NEloc + EB - 1) / EB;
         c->grid = (int)std::min<long long>(nbatch, (long long)prop.multiProcessorCount * occ);
@@ -371,7 +452,7 @@ int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
     const size_t hn = std::max<size_t>(1, (size_t)6 * H.n_halo_faces * H.Nfp);
     c->halo.alloc(hn); c->sendbuf.alloc(hn); c->scratch.alloc(4);
     CU(cudaMemset(c->halo.p, 0, hn * sizeof(double)));
-    const size_t n6 = (size_t)6 * c->Nloc;
+    const size_t n6 = (size_t)6 * c->Nalloc;
     c->x.alloc(n6); c->ya.alloc(n6); c->yb.alloc(n6); c->z.alloc(n6);
     CU(cudaMemset(c->x.p, 0, n6 * sizeof(double))); CU(cudaMemset(c->ya.p, 0, n6 * sizeof(double)));
     CU(cudaMemset(c->yb.p, 0, n6 * sizeof(double))); CU(cudaMemset(c->z.p, 0, n6 * sizeof(double)));
@@ -438,8 +519,7 @@ int dgtd_set_state_local(dgtd_ctx *c, const double *h)
     GUARD_BEGIN
     if (!c || !h) throw Error(DGTD_ERR_ARG, "null argument");
     CU(cudaSetDevice(c->device));
-    CU(cudaMemcpyAsync(c->x.p, h, sizeof(double) * 6 * c->Nloc, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    upload_local(c, h, c->x.p);
     GUARD_END
 }
 int dgtd_get_state_local(dgtd_ctx *c, double *h)
@@ -447,8 +527,7 @@ int dgtd_get_state_local(dgtd_ctx *c, double *h)
     GUARD_BEGIN
     if (!c || !h) throw Error(DGTD_ERR_ARG, "null argument");
     CU(cudaSetDevice(c->device));
-    CU(cudaMemcpyAsync(h, c->x.p, sizeof(double) * 6 * c->Nloc, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    download_local(c, c->x.p, h);
     GUARD_END
 }
 int dgtd_state_device_ptr(dgtd_ctx *c, double **dev)
@@ -462,13 +541,20 @@ int dgtd_mult(dgtd_ctx *c, double t, const double *in, double *out, int on_devic
     GUARD_BEGIN
     if (!c || !in || !out) throw Error(DGTD_ERR_ARG, "null argument");
     CU(cudaSetDevice(c->device));
-    if (on_device) { mult_device(c, t, in, out); }
+    const size_t n6 = (size_t)6 * c->Nalloc;
+    if (on_device && !c->blocked) { mult_device(c, t, in, out); }
     else {
-        const size_t n6 = (size_t)6 * c->Nloc;
         if (c->tmp_in.n != n6) { c->tmp_in.alloc(n6); c->tmp_out.alloc(n6); }
-        scatter_to_device(c, in, c->tmp_in.p);
-        mult_device(c, t, c->tmp_in.p, c->tmp_out.p);
-        gather_from_device(c, c->tmp_out.p, out);
+        if (on_device) {   // reference-layout device vectors [6][n_local] <-> blocked
+            to_blocked_kernel<<<1184, 256, 0, c->stream>>>(in, c->Nloc, c->H.Np, c->H.NEloc, c->BP.NEpad, c->tmp_in.p);
+            mult_device(c, t, c->tmp_in.p, c->tmp_out.p);
+            from_blocked_kernel<<<1184, 256, 0, c->stream>>>(c->tmp_out.p, c->Nloc, c->H.Np, c->H.NEloc, out);
+            c->launches += 2;
+        } else {
+            scatter_to_device(c, in, c->tmp_in.p);
+            mult_device(c, t, c->tmp_in.p, c->tmp_out.p);
+            gather_from_device(c, c->tmp_out.p, out);
+        }
     }
     GUARD_END
 }
@@ -495,7 +581,7 @@ int dgtd_norm2_local(dgtd_ctx *c, double *sumsq)
     if (!c || !sumsq) throw Error(DGTD_ERR_ARG, "null argument");
     CU(cudaSetDevice(c->device));
     CU(cudaMemsetAsync(c->scratch.p, 0, sizeof(double), c->stream));
-    sumsq_kernel<<<296, 256, 0, c->stream>>>(c->x.p, 6 * c->Nloc, c->scratch.p);
+    sumsq_kernel<<<296, 256, 0, c->stream>>>(c->x.p, 6 * c->Nalloc, c->scratch.p);
     c->launches++;
     CU(cudaMemcpyAsync(sumsq, c->scratch.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -512,7 +598,8 @@ int dgtd_sample(dgtd_ctx *c, int npts, const int *elem, const double *shape, dou
     de.alloc(npts); ds.alloc((size_t)npts * c->H.Np); dout.alloc((size_t)npts * 6);
     CU(cudaMemcpyAsync(de.p, elem, sizeof(int) * npts, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(ds.p, shape, sizeof(double) * npts * c->H.Np, cudaMemcpyHostToDevice, c->stream));
-    sample_kernel<<<(npts + 127) / 128, 128, 0, c->stream>>>(c->x.p, c->Nloc, c->H.Np, npts, de.p, ds.p, dout.p);
+    if (c->blocked) sample_blocked_kernel<<<(npts + 127) / 128, 128, 0, c->stream>>>(c->x.p, c->H.Np, npts, de.p, ds.p, dout.p);
+    else sample_kernel<<<(npts + 127) / 128, 128, 0, c->stream>>>(c->x.p, c->Nloc, c->H.Np, npts, de.p, ds.p, dout.p);
     c->launches++;
     CU(cudaMemcpyAsync(out6, dout.p, sizeof(double) * npts * 6, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));

@@ -85,6 +85,7 @@ struct HostOp {
     RefElem ref;
     std::vector<int> elem_gid;            // NEloc
     std::vector<double> geo;              // NEloc*GEO_STRIDE
+    std::vector<double> jac;              // NEloc*10 : J[d][a] = dx_d/dxi_a (3d+a), det J
     std::vector<int> finfo;               // NEloc*4*2 : {nbr local element | -1 boundary | -2-haloFace, code}
     std::vector<uint8_t> ftab;            // ntab*Nfp
     int ntab = 0;
@@ -103,6 +104,27 @@ struct HostOp {
     bool tfsf_gate = true;
 };
 HostOp build_host_op(const Mesh &m, const Options &o);
+
+// ---- "blocked" plan of the DMMA stage kernel (3-D only) ----------------------------------------------------------------
+// Device state layout: groups of 8 consecutive local elements; group g holds Np*8*6 doubles indexed [node j][e8][comp c]
+// (a node's six field components are contiguous: one 48-byte record).  A batch = G groups is what one CTA pass handles.
+constexpr int BLK_E = 8;               // elements per group (= DMMA n dimension)
+constexpr int BLK_GEO = 32;            // doubles per element: J[9] (dx_d/dxi_a at 3d+a), Jinv[9] (dxi_a/dx_d at 9+3a+d),
+                                       //   fscale[4] at 18, 1/detJ at 22, 1/eps 23, 1/mu 24, sigma/eps 25
+struct BlockedPlan {
+    int G = 1;                         // groups per batch
+    int ngroups = 0, nbatch = 0, NEpad = 0;
+    int slots = 0;                     // trace slots per batch (= 4 * 8 * G, the worst case)
+    int MT = 0, KSV = 0, KSL = 0;      // m-tiles, k-steps of one volume half (D_x), k-steps of LIFT
+    std::vector<double> geo;           // NEpad * BLK_GEO
+    std::vector<int> finfo;            // NEpad*4*2 : {>=0 in-batch element | -1 boundary | -2-slot, code}
+    std::vector<int> tdesc;            // nbatch*slots*2 : {>=0 source local element | -1-haloFace, ftab row}
+    std::vector<int> tcount;           // nbatch : used slots
+    std::vector<double> afrag;         // DMMA A fragments: D_x [3][MT][KSV][32] then 0.5*LIFT [MT][KSL][32]
+    std::vector<long long> send_off;   // nSendFaces*Nfp : offset (doubles) of the node record in the blocked state
+};
+BlockedPlan build_blocked_plan(const HostOp &H, int G);
+inline long long blocked_offset(int Np, long long le, int node) { return (((le >> 3) * Np + node) * BLK_E + (le & 7)) * 6; }
 void node_coords(const Mesh &m, const RefElem &ref, std::vector<double> &xyz);   // [NE*Np][3], global numbering
 
 }  // namespace dgtd

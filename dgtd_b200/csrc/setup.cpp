@@ -52,6 +52,41 @@ void elem_geometry(const Mesh &m, int e, double J[3][3], double Jinv[3][3], doub
     // Jinv[xi][d] = d xi / d x_d
 }
 
+// Sort the rank's elements along a Morton curve of their barycentres, quantised to about one element diameter
+// (ties keep the mesh order, so the six tetrahedra of a Kuhn cube stay together).
+void morton_order(const Mesh &m, std::vector<int> &ids)
+{
+    const int nf = m.dim + 1, n = (int)ids.size();
+    if (n < 2) return;
+    std::vector<double> bc(3 * (size_t)n, 0.0);
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int i = 0; i < n; i++)
+        for (int c = 0; c < 3; c++) {
+            double s = 0;
+            for (int k = 0; k < nf; k++) s += m.verts[3 * (size_t)m.elems[(size_t)ids[i] * nf + k] + c];
+            s /= nf; bc[3 * (size_t)i + c] = s;
+            lo[c] = std::min(lo[c], s); hi[c] = std::max(hi[c], s);
+        }
+    double vol = 1.0; int nd = 0;
+    for (int c = 0; c < 3; c++) if (hi[c] - lo[c] > 0) { vol *= hi[c] - lo[c]; nd++; }
+    if (nd == 0) return;
+    const double cell = 1.817 * std::pow(vol / n, 1.0 / nd);
+    auto spread = [](uint64_t v) {   // 21 bits -> every third bit
+        v &= 0x1fffff;
+        v = (v | v << 32) & 0x1f00000000ffffULL; v = (v | v << 16) & 0x1f0000ff0000ffULL; v = (v | v << 8) & 0x100f00f00f00f00fULL;
+        v = (v | v << 4) & 0x10c30c30c30c30c3ULL; v = (v | v << 2) & 0x1249249249249249ULL;
+        return v;
+    };
+    std::vector<std::pair<uint64_t, int>> key(n);
+    for (int i = 0; i < n; i++) {
+        uint64_t q[3];
+        for (int c = 0; c < 3; c++) q[c] = (uint64_t)std::min(2097151.0, std::floor((bc[3 * (size_t)i + c] - lo[c]) / cell + 1e-9));
+        key[i] = {spread(q[0]) | spread(q[1]) << 1 | spread(q[2]) << 2, ids[i]};
+    }
+    std::stable_sort(key.begin(), key.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+    for (int i = 0; i < n; i++) ids[i] = key[i].second;
+}
+
 }  // namespace
 
 void node_coords(const Mesh &m, const RefElem &ref, std::vector<double> &xyz)
@@ -200,9 +235,11 @@ HostOp build_host_op(const Mesh &m, const Options &o)
         for (int r : part) if (r < 0 || r >= o.nranks) throw Error(DGTD_ERR_ARG, "partitioning entry out of range");
     } else part.assign(NE, 0);
     std::vector<int> g2l(NE, -1);
-    for (int e = 0; e < NE; e++) if (part[e] == o.rank) { g2l[e] = (int)H.elem_gid.size(); H.elem_gid.push_back(e); }
+    for (int e = 0; e < NE; e++) if (part[e] == o.rank) H.elem_gid.push_back(e);
     const int NEloc = H.NEloc = (int)H.elem_gid.size();
     if (NEloc == 0) throw Error(DGTD_ERR_ARG, "rank owns no elements");
+    if (dim == 3) morton_order(m, H.elem_gid);   // locality: consecutive local elements are spatial neighbours
+    for (int le = 0; le < NEloc; le++) g2l[H.elem_gid[le]] = le;
     // shared faces, ordered per peer by (owner-of-lower-rank element id, its face): both sides enumerate identically
     struct Shared { int peer, keyE, keyF, le, f, ge2, f2; };
     std::vector<Shared> shared;
@@ -240,6 +277,7 @@ HostOp build_host_op(const Mesh &m, const Options &o)
         mats[kv.first] = kv.second;
     }
     H.geo.assign((size_t)NEloc * GEO_STRIDE, 0.0);
+    H.jac.assign((size_t)NEloc * 10, 0.0);
     H.finfo.assign((size_t)NEloc * 4 * 2, 0);
     H.tfsf_side.assign(NEloc, 0);
     std::vector<double> xyzTF;
@@ -250,6 +288,8 @@ HostOp build_host_op(const Mesh &m, const Options &o)
         if (!(det > 0)) throw Error(DGTD_ERR_MESH, "element with non-positive Jacobian");
         double *g = &H.geo[(size_t)le * GEO_STRIDE];
         for (int x = 0; x < 3; x++) for (int d = 0; d < 3; d++) g[3 * x + d] = Ji[x][d];
+        for (int d = 0; d < 3; d++) for (int a = 0; a < 3; a++) H.jac[(size_t)le * 10 + 3 * d + a] = J[d][a];
+        H.jac[(size_t)le * 10 + 9] = det;
         for (int f = 0; f < nf; f++) {   // |grad lambda_f| = |J_f| / |J_e|
             double gl[3];
             for (int d = 0; d < 3; d++) {
