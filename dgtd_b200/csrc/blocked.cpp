@@ -41,21 +41,24 @@ BlockedPlan build_blocked_plan(const HostOp &H, int G)
         }
     }
     // ---- faces: in-batch neighbour, boundary, or a trace slot filled by the prefetch -------------------------------
-    B.finfo.assign((size_t)B.NEpad * 4 * 2, 0);
-    B.tdesc.assign((size_t)B.nbatch * B.slots * 2, 0);
-    B.tcount.assign(B.nbatch, 0);
+    // per batch one descriptor block: finfo int2[EB*4] {>=0 in-batch element | -1 boundary | -2-slot, code},
+    // tdesc int2[slots] {>=0 source local element | -1-haloFace, ftab row}, used-slot count, 3 pad ints
+    B.desc_stride = EB * 8 + B.slots * 2 + 4;
+    B.desc.assign((size_t)B.nbatch * B.desc_stride, 0);
     for (int e = 0; e < B.NEpad; e++) {
         const int b = e / EB;
+        int *blk = &B.desc[(size_t)b * B.desc_stride];
+        int *tcount = blk + EB * 8 + B.slots * 2;
         for (int f = 0; f < 4; f++) {
-            int *fo = &B.finfo[((size_t)e * 4 + f) * 2];
+            int *fo = blk + ((size_t)(e - b * EB) * 4 + f) * 2;
             if (e >= NE) { fo[0] = -1; fo[1] = f << FI_TAB_SHIFT; continue; }   // boundary with BC none: zero jump
             const int nb = H.finfo[((size_t)e * 4 + f) * 2], code = H.finfo[((size_t)e * 4 + f) * 2 + 1];
             fo[1] = code;
             if (nb == -1) fo[0] = -1;
             else if (nb >= 0 && nb / EB == b) fo[0] = nb - b * EB;
             else {
-                const int s = B.tcount[b]++;
-                int *td = &B.tdesc[((size_t)b * B.slots + s) * 2];
+                const int s = (*tcount)++;
+                int *td = blk + EB * 8 + (size_t)s * 2;
                 td[0] = nb >= 0 ? nb : -1 - (-2 - nb);      // local element, or -1-haloFace
                 td[1] = (code >> FI_TAB_SHIFT) & FI_TAB_MASK;
                 fo[0] = -2 - s;

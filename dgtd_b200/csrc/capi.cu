@@ -133,7 +133,7 @@ struct dgtd_ctx {
     long long Nalloc = 0;            // scalar dofs allocated per component (padded to whole batches when blocked)
     MmaSet ms{};
     DevBuf<double> bgeo, bafrag, stage_ref;
-    DevBuf<int> bfinfo, btdesc, btcount;
+    DevBuf<int> bdesc;
     DevBuf<long long> bsend_off;
     Mesh mesh;                       // kept for node_coords
     int device = 0;
@@ -210,8 +210,7 @@ static void launch_stage(dgtd_ctx *c, int mode, StageArgs &A)
     exchange(c, A.yin);
     if (c->blocked) {
         MmaArgs M;
-        M.afrag = c->bafrag.p; M.geo = c->bgeo.p; M.finfo = reinterpret_cast<const int2 *>(c->bfinfo.p);
-        M.tdesc = reinterpret_cast<const int2 *>(c->btdesc.p); M.tcount = c->btcount.p; M.ftab = c->ftab.p; M.ntab = c->H.ntab;
+        M.afrag = c->bafrag.p; M.geo = c->bgeo.p; M.desc = c->bdesc.p; M.ftab = c->ftab.p; M.ntab = c->H.ntab;
         M.tfsf_xyz = A.tfsf_xyz; M.gate = A.gate; M.halo = A.halo; M.nbatch = c->BP.nbatch; M.alpha = A.alpha; M.pw = A.pw; M.pw_on = A.pw_on;
         M.yin = A.yin; M.x = A.x; M.z = A.z; M.yout = A.yout; M.a = A.a; M.b = A.b; M.t = A.t;
         c->ms.fn[mode]<<<c->grid, c->ms.threads, c->ms.smem, c->stream>>>(M);
@@ -422,8 +421,7 @@ int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
         int occ = 0; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)c->ms.fn[2], c->ms.threads, c->ms.smem));
         if (occ < 1) throw Error(DGTD_ERR_UNSUPPORTED, "DMMA stage kernel does not fit on an SM");
         c->grid = (int)std::min<long long>(c->BP.nbatch, (long long)prop.multiProcessorCount * occ);
-        c->bgeo.upload(c->BP.geo); c->bafrag.upload(c->BP.afrag); c->bfinfo.upload(c->BP.finfo);
-        c->btdesc.upload(c->BP.tdesc); c->btcount.upload(c->BP.tcount); c->bsend_off.upload(c->BP.send_off, 1);
+        c->bgeo.upload(c->BP.geo); c->bafrag.upload(c->BP.afrag); c->bdesc.upload(c->BP.desc); c->bsend_off.upload(c->BP.send_off, 1);
     } else {
         c->Nalloc = c->Nloc;
         c->ks = select_kernels(H.dim, H.p);

@@ -117,9 +117,8 @@ struct BlockedPlan {
     int slots = 0;                     // trace slots per batch (= 4 * 8 * G, the worst case)
     int MT = 0, KSV = 0, KSL = 0;      // m-tiles, k-steps of one volume half (D_x), k-steps of LIFT
     std::vector<double> geo;           // NEpad * BLK_GEO
-    std::vector<int> finfo;            // NEpad*4*2 : {>=0 in-batch element | -1 boundary | -2-slot, code}
-    std::vector<int> tdesc;            // nbatch*slots*2 : {>=0 source local element | -1-haloFace, ftab row}
-    std::vector<int> tcount;           // nbatch : used slots
+    int desc_stride = 0;               // ints per batch descriptor block
+    std::vector<int> desc;             // nbatch*desc_stride : finfo int2[8G*4], tdesc int2[slots], tcount, 3 pad (see blocked.cpp)
     std::vector<double> afrag;         // DMMA A fragments: D_x [3][MT][KSV][32] then 0.5*LIFT [MT][KSL][32]
     std::vector<long long> send_off;   // nSendFaces*Nfp : offset (doubles) of the node record in the blocked state
 };

@@ -20,9 +20,7 @@ namespace dgtd {
 struct MmaArgs {
     const double *afrag;      // DMMA A fragments (BlockedPlan::afrag)
     const double *geo;        // [NEpad][32]
-    const int2 *finfo;        // [NEpad][4]
-    const int2 *tdesc;        // [nbatch][slots]
-    const int *tcount;        // [nbatch]
+    const int *desc;          // [nbatch][DS] per-batch descriptors: finfo int2[EB*4], tdesc int2[SL], tcount, 3 pad
     const uint8_t *ftab;      // [ntab][Nfp]
     int ntab;
     const double *tfsf_xyz;
@@ -81,14 +79,22 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// bank swizzle of the [row][8 elements] operand tiles: a DMMA B-fragment load touches rows 4ks..4ks+3 x elements
+// (lane>>2); flipping bit 2 of the element index on rows with bit 1 set spreads a half-warp over all 16 bank pairs
+__device__ __forceinline__ int swz8(int row, int e) { return row * BLK_E + (e ^ ((row & 2) << 1)); }
+
 template <int P, int G> struct Blk {
     static constexpr int Np = (P + 1) * (P + 2) * (P + 3) / 6, Nfp = (P + 1) * (P + 2) / 2, NFN = 4 * Nfp;
     static constexpr int MT = (Np + 7) / 8, KSV = (Np + 3) / 4, KH = 4 * KSV, KSL = NFN / 4;
     static constexpr int EB = BLK_E * G, NW = 6 * G, T = 32 * NW;
     static constexpr int GS = Np * BLK_E * 6;                 // doubles per group of one state vector
     static constexpr int SL = 4 * EB;                         // trace slots per batch
+    static constexpr int DS = EB * 8 + SL * 2 + 4;            // ints per batch descriptor block (multiple of 4)
     static constexpr int TABROWS = 128;
-    static constexpr int NA = (3 * MT * KSV + MT * KSL) * 32;
+    static constexpr int GST = BLK_GEO + 2;                   // geometry record stride in shared memory (bank spread over the 8 elements of a group)
+    static constexpr bool AREG = 2 * MT * KSV <= 32;          // volume A fragments live in registers (else in shared memory)
+    static constexpr int NAV = 3 * MT * KSV * 32, NAL = MT * KSL * 32;
+    static constexpr int NA = (AREG ? 0 : NAV) + NAL;
     // shared-memory carve-up (doubles)
     static constexpr int oRaw = 0;                            // [2][G*GS]   stage input as it lies in HBM
     static constexpr int oU = oRaw + 2 * G * GS;              // [G][6][KH][8]  covariant field (E negated) ; later: yout staging
@@ -96,15 +102,16 @@ template <int P, int G> struct Blk {
     static constexpr int oX = oF + G * 6 * NFN * 8;           // [G*GS]
     static constexpr int oZ = oX + G * GS;                    // [G*GS]
     static constexpr int oTr = oZ + G * GS;                   // [2][SL][Nfp][6]
-    static constexpr int oGeo = oTr + 2 * SL * Nfp * 6;       // [2][EB][32]
-    static constexpr int oA = oGeo + 2 * EB * BLK_GEO;        // [NA]
+    static constexpr int oGeo = oTr + 2 * SL * Nfp * 6;       // [3][EB][GST]
+    static constexpr int oA = oGeo + 3 * EB * GST;            // [NA]
     static constexpr int nDoubles = oA + NA;
-    static constexpr size_t bFi = (size_t)nDoubles * 8;       // int2 [2][EB*4]
-    static constexpr size_t bTab = bFi + (size_t)2 * EB * 4 * 8;
+    static constexpr size_t bDesc = (size_t)nDoubles * 8;     // int [3][DS]
+    static constexpr size_t bTab = bDesc + (size_t)3 * DS * 4;
     static constexpr size_t bBar = bTab + (size_t)TABROWS * Nfp;   // 128*Nfp is a multiple of 8
     static constexpr size_t smem_bytes = bBar + 4 * 8;
     static_assert(6 * KH * 8 >= GS, "yout staging must fit in the U buffer");
     static_assert(NFN >= Np, "k must fit in the head rows of its flux slice");
+    static_assert((oA % 2) == 0 && (bDesc % 16) == 0 && (bBar % 8) == 0, "alignment");
 };
 
 template <int P, int G, int MODE>
@@ -112,7 +119,7 @@ __global__ void __launch_bounds__(Blk<P, G>::T, G == 1 ? 2 : 1) stage_mma_kernel
 {
     using B = Blk<P, G>;
     constexpr int Np = B::Np, Nfp = B::Nfp, NFN = B::NFN, MT = B::MT, KSV = B::KSV, KH = B::KH, KSL = B::KSL;
-    constexpr int EB = B::EB, NW = B::NW, T = B::T, GS = B::GS, SL = B::SL;
+    constexpr int EB = B::EB, NW = B::NW, T = B::T, GS = B::GS, SL = B::SL, GST = B::GST, DS = B::DS;
     constexpr uint32_t BATCH_BYTES = (uint32_t)G * GS * 8;
     constexpr bool LOAD_X = MODE == MODE_STAGE23, LOAD_Z = MODE == MODE_STAGE23 || MODE == MODE_STAGE4;
     constexpr bool STORE_Z = MODE == MODE_STAGE1 || MODE == MODE_STAGE23;
@@ -120,43 +127,59 @@ __global__ void __launch_bounds__(Blk<P, G>::T, G == 1 ? 2 : 1) stage_mma_kernel
     unsigned char *smem_raw = smem_mma;
     double *sm = reinterpret_cast<double *>(smem_raw);
     double *sU = sm + B::oU, *sF = sm + B::oF, *sX = sm + B::oX, *sZ = sm + B::oZ, *sA = sm + B::oA;
-    int2 *sFi = reinterpret_cast<int2 *>(smem_raw + B::bFi);
+    int *sDesc = reinterpret_cast<int *>(smem_raw + B::bDesc);
     uint8_t *sTab = smem_raw + B::bTab;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + B::bBar);   // [0],[1]: stage input buffers ; [2]: x/z
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < B::NA; i += T) sA[i] = A.afrag[i];
     {
+        const double *asrc = A.afrag + (B::AREG ? B::NAV : 0);
+        for (int i = tid; i < B::NA; i += T) sA[i] = asrc[i];
         const int nb = min(A.ntab, B::TABROWS) * Nfp;
         for (int i = tid; i < nb; i += T) sTab[i] = A.ftab[i];
     }
-    for (int i = tid; i < G * 6 * KH * 8; i += T) sU[i] = 0.0;           // rows Np..KH-1 stay zero (k padding of the DMMA)
     if (tid == 0) {
         mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
     }
-    __syncthreads();
+    // this warp's output tile type is fixed: field f (0: dE/dt rows, 1: dH/dt rows), reference component cp
+    const int wr = warp % 6, wf = wr / 3, cp = wr - 3 * wf;
+    const int c1 = (cp + 2) % 3, x1 = (cp + 1) % 3;
+    double aV[B::AREG ? 2 * MT * KSV : 1];
+    if (B::AREG) {
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+            for (int ks = 0; ks < KSV; ks++) {
+                aV[mt * KSV + ks] = __ldg(A.afrag + ((x1 * MT + mt) * KSV + ks) * 32 + lane);
+                aV[(MT + mt) * KSV + ks] = __ldg(A.afrag + ((c1 * MT + mt) * KSV + ks) * 32 + lane);
+            }
+    }
     const bool inject = A.pw_on && (A.gate == nullptr || *A.gate >= 1e-16);
 
-    // everything batch `bb` needs from HBM/L2 except x and z, into buffer `bf`
-    auto prefetch = [&](int bb, int bf) {
+    // stage 1 of the prefetch (two batches ahead): geometry records and the batch descriptor block, plain copies
+    auto prefetch_desc = [&](int bb, int ring) {
+        const double *gsrc = A.geo + (size_t)bb * EB * BLK_GEO;
+        double *gdst = sm + B::oGeo + ring * EB * GST;
+        for (int i = tid; i < EB * BLK_GEO / 2; i += T) cp_async16(gdst + (i / (BLK_GEO / 2)) * GST + 2 * (i % (BLK_GEO / 2)), gsrc + 2 * i);
+        const int *dsrc = A.desc + (size_t)bb * DS;
+        int *ddst = sDesc + ring * DS;
+        for (int i = tid; i < DS / 4; i += T) cp_async16(ddst + 4 * i, dsrc + 4 * i);
+    };
+    // stage 2 (one batch ahead): the stage input by bulk TMA, the traces of faces leaving the batch by cp.async
+    auto prefetch_data = [&](int bb, int bf, int ring) {
         if (tid == 0) {
             mbar_expect_tx(&bars[bf], BATCH_BYTES);
             bulk_load(sm + B::oRaw + bf * G * GS, A.yin + (size_t)bb * G * GS, BATCH_BYTES, &bars[bf]);
         }
-        const double *gsrc = A.geo + (size_t)bb * EB * BLK_GEO;
-        double *gdst = sm + B::oGeo + bf * EB * BLK_GEO;
-        for (int i = tid; i < EB * BLK_GEO / 2; i += T) cp_async16(gdst + 2 * i, gsrc + 2 * i);
-        const char *fsrc = reinterpret_cast<const char *>(A.finfo + (size_t)bb * EB * 4);
-        char *fdst = reinterpret_cast<char *>(sFi + bf * EB * 4);
-        for (int i = tid; i < EB * 2; i += T) cp_async16(fdst + 16 * i, fsrc + 16 * i);
-        const int nt = __ldg(A.tcount + bb);
-        const int2 *td = A.tdesc + (size_t)bb * SL;
+        const int *dsc = sDesc + ring * DS;
+        const int nt = dsc[EB * 8 + SL * 2];
+        const int2 *td = reinterpret_cast<const int2 *>(dsc + EB * 8);
         double *tdst = sm + B::oTr + bf * SL * Nfp * 6;
         for (int it = tid; it < nt * Nfp * 3; it += T) {
             const int slot = it / (Nfp * 3), r = it - slot * (Nfp * 3), m = r / 3, ch = r - 3 * m;
-            const int2 d = __ldg(td + slot);
+            const int2 d = td[slot];
             const double *src;
             if (d.x >= 0) {
                 const int nn = sTab[d.y * Nfp + m];
@@ -164,17 +187,25 @@ __global__ void __launch_bounds__(Blk<P, G>::T, G == 1 ? 2 : 1) stage_mma_kernel
             } else src = A.halo + ((size_t)(-1 - d.x) * Nfp + m) * 6;
             cp_async16(tdst + (slot * Nfp + m) * 6 + 2 * ch, src + 2 * ch);
         }
-        cp_async_commit();
     };
 
     int b = blockIdx.x;
-    if (b < A.nbatch) prefetch(b, 0);
-    for (int it = 0; b < A.nbatch; b += gridDim.x, it++) {
+    const int gstep = gridDim.x;
+    if (b < A.nbatch) prefetch_desc(b, 0);
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+    if (b < A.nbatch) prefetch_data(b, 0, 0);
+    if (b + gstep < A.nbatch) prefetch_desc(b + gstep, 1);
+    cp_async_commit();
+    int ring = 0;
+    for (int it = 0; b < A.nbatch; b += gstep, it++) {
         const int cur = it & 1;
+        const int ring1 = ring == 2 ? 0 : ring + 1, ring2 = ring1 == 2 ? 0 : ring1 + 1;
         const double *raw = sm + B::oRaw + cur * G * GS;
         const double *tr = sm + B::oTr + cur * SL * Nfp * 6;
-        const double *geo = sm + B::oGeo + cur * EB * BLK_GEO;
-        const int2 *fi = sFi + cur * EB * 4;
+        const double *geo = sm + B::oGeo + ring * EB * GST;
+        const int2 *fi = reinterpret_cast<const int2 *>(sDesc + ring * DS);
         cp_async_wait_all();
         mbar_wait(&bars[cur], (it >> 1) & 1);
         if (tid == 0) bulk_wait_read();          // the previous batch's stores have drained their staging buffers
@@ -184,7 +215,9 @@ __global__ void __launch_bounds__(Blk<P, G>::T, G == 1 ? 2 : 1) stage_mma_kernel
             if (LOAD_X) bulk_load(sX, A.x + (size_t)b * G * GS, BATCH_BYTES, &bars[2]);
             if (LOAD_Z) bulk_load(sZ, A.z + (size_t)b * G * GS, BATCH_BYTES, &bars[2]);
         }
-        if (b + (int)gridDim.x < A.nbatch) prefetch(b + gridDim.x, cur ^ 1);
+        if (b + gstep < A.nbatch) prefetch_data(b + gstep, cur ^ 1, ring1);
+        if (b + 2 * gstep < A.nbatch) prefetch_desc(b + 2 * gstep, ring2);
+        cp_async_commit();
 
         // ---- face flux: jumps, boundary ghost states, TF/SF, upwind flux, pulled back to reference components -------
         for (int item = tid; item < EB * NFN; item += T) {
@@ -228,7 +261,7 @@ __global__ void __launch_bounds__(Blk<P, G>::T, G == 1 ? 2 : 1) stage_mma_kernel
 #pragma unroll
                 for (int c = 0; c < 6; c++) dU[c] += sg * inc[c];
             }
-            const double *ge = geo + el * BLK_GEO;
+            const double *ge = geo + el * GST;
             const double *ji = ge + 9;              // Jinv[a][d] at 3a+d
             double gn[3];                           // outward normal * fscale = -grad lambda_f
 #pragma unroll
@@ -245,7 +278,7 @@ __global__ void __launch_bounds__(Blk<P, G>::T, G == 1 ? 2 : 1) stage_mma_kernel
             fl[3] = -(gn[1] * dU[2] - gn[2] * dU[1]) + af * (dU[3] - gdH * gn[0]);
             fl[4] = -(gn[2] * dU[0] - gn[0] * dU[2]) + af * (dU[4] - gdH * gn[1]);
             fl[5] = -(gn[0] * dU[1] - gn[1] * dU[0]) + af * (dU[5] - gdH * gn[2]);
-            double *pf = sF + ((g * 6) * NFN + f * Nfp + m) * BLK_E + e8;
+            double *pf = sF + (g * 6) * NFN * BLK_E + swz8(f * Nfp + m, e8);
 #pragma unroll
             for (int a = 0; a < 3; a++) {
                 pf[a * NFN * BLK_E] = fma(ji[3 * a], fl[0], fma(ji[3 * a + 1], fl[1], ji[3 * a + 2] * fl[2]));
@@ -253,18 +286,18 @@ __global__ void __launch_bounds__(Blk<P, G>::T, G == 1 ? 2 : 1) stage_mma_kernel
             }
         }
         // ---- covariant field  u~ = J^T u / det J  (E stored negated: it only feeds dH/dt = -curl E) ----------------
-        for (int item = tid; item < EB * KH; item += T) {
+        for (int item = T - 1 - tid; item < EB * KH; item += T) {
             const int e8 = item & 7, r = item >> 3, j = r % KH, g = r / KH, el = g * BLK_E + e8;
+            double *po = sU + (g * 6) * KH * BLK_E + swz8(j, e8);
             if (KH > Np && j >= Np) {   // k-padding rows of the DMMA (the yout staging of the previous batch lay here)
 #pragma unroll
-                for (int c = 0; c < 6; c++) sU[((g * 6 + c) * KH + j) * BLK_E + e8] = 0.0;
+                for (int c = 0; c < 6; c++) po[c * KH * BLK_E] = 0.0;
                 continue;
             }
             const double2 *pu = reinterpret_cast<const double2 *>(raw + ((g * Np + j) * BLK_E + e8) * 6);
             const double2 v0 = pu[0], v1 = pu[1], v2 = pu[2];
-            const double *ge = geo + el * BLK_GEO;   // J[d][a] at 3d+a
+            const double *ge = geo + el * GST;   // J[d][a] at 3d+a
             const double idet = ge[22], nidet = -idet;
-            double *po = sU + ((g * 6) * KH + j) * BLK_E + e8;
 #pragma unroll
             for (int a = 0; a < 3; a++) {
                 po[a * KH * BLK_E] = fma(ge[a], v0.x, fma(ge[3 + a], v0.y, ge[6 + a] * v1.x)) * nidet;
@@ -275,10 +308,9 @@ __global__ void __launch_bounds__(Blk<P, G>::T, G == 1 ? 2 : 1) stage_mma_kernel
 
         // ---- contraction: k~[i][e] = sum_j D_{c+1}[i][j] u~_{c+2}[j][e] - D_{c+2}[i][j] u~_{c+1}[j][e] + LIFT/2 [i][m] F~_c[m][e] ----
         for (int tile = warp; tile < 6 * G; tile += NW) {
-            const int g = tile / 6, r = tile - 6 * g, f = r / 3, cp = r - 3 * f;
-            const int c1 = (cp + 2) % 3, x1 = (cp + 1) % 3;
-            const double *Ub = sU + ((g * 6 + (1 - f) * 3) * KH) * BLK_E;
-            const int boff = (lane & 3) * BLK_E + (lane >> 2);
+            const int g = tile / 6;
+            const double *Ub = sU + ((g * 6 + (1 - wf) * 3) * KH) * BLK_E;
+            const int boff = (lane & 3) * BLK_E + ((lane >> 2) ^ ((lane & 2) << 1));   // swz8(4ks + (lane&3), lane>>2) - 32 ks
             double acc[MT][2];
 #pragma unroll
             for (int mt = 0; mt < MT; mt++) acc[mt][0] = acc[mt][1] = 0.0;
@@ -286,16 +318,18 @@ __global__ void __launch_bounds__(Blk<P, G>::T, G == 1 ? 2 : 1) stage_mma_kernel
             for (int ks = 0; ks < KSV; ks++) {
                 const double bv = Ub[(c1 * KH + 4 * ks) * BLK_E + boff];
 #pragma unroll
-                for (int mt = 0; mt < MT; mt++) dmma884(acc[mt][0], acc[mt][1], sA[((x1 * MT + mt) * KSV + ks) * 32 + lane], bv);
+                for (int mt = 0; mt < MT; mt++)
+                    dmma884(acc[mt][0], acc[mt][1], B::AREG ? aV[mt * KSV + ks] : sA[((x1 * MT + mt) * KSV + ks) * 32 + lane], bv);
             }
 #pragma unroll
             for (int ks = 0; ks < KSV; ks++) {
                 const double bv = -Ub[(x1 * KH + 4 * ks) * BLK_E + boff];
 #pragma unroll
-                for (int mt = 0; mt < MT; mt++) dmma884(acc[mt][0], acc[mt][1], sA[((c1 * MT + mt) * KSV + ks) * 32 + lane], bv);
+                for (int mt = 0; mt < MT; mt++)
+                    dmma884(acc[mt][0], acc[mt][1], B::AREG ? aV[(MT + mt) * KSV + ks] : sA[((c1 * MT + mt) * KSV + ks) * 32 + lane], bv);
             }
-            double *Fb = sF + ((g * 6 + 3 * f + cp) * NFN) * BLK_E;
-            const double *sL = sA + 3 * MT * KSV * 32;
+            double *Fb = sF + ((g * 6 + 3 * wf + cp) * NFN) * BLK_E;
+            const double *sL = sA + (B::AREG ? 0 : B::NAV);
 #pragma unroll
             for (int ks = 0; ks < KSL; ks++) {
                 const double bv = Fb[4 * ks * BLK_E + boff];
@@ -306,7 +340,7 @@ __global__ void __launch_bounds__(Blk<P, G>::T, G == 1 ? 2 : 1) stage_mma_kernel
 #pragma unroll
             for (int mt = 0; mt < MT; mt++) {
                 const int i = mt * 8 + (lane >> 2);
-                if (i < Np) *reinterpret_cast<double2 *>(Fb + i * BLK_E + 2 * (lane & 3)) = make_double2(acc[mt][0], acc[mt][1]);
+                if (i < Np) *reinterpret_cast<double2 *>(Fb + swz8(i, 2 * (lane & 3))) = make_double2(acc[mt][0], acc[mt][1]);
             }
         }
         __syncthreads();
@@ -315,11 +349,11 @@ __global__ void __launch_bounds__(Blk<P, G>::T, G == 1 ? 2 : 1) stage_mma_kernel
         if (LOAD_X || LOAD_Z) mbar_wait(&bars[2], it & 1);
         for (int item = tid; item < EB * Np; item += T) {
             const int e8 = item & 7, r = item >> 3, i = r % Np, g = r / Np, el = g * BLK_E + e8;
-            const double *pk = sF + ((g * 6) * NFN + i) * BLK_E + e8;
+            const double *pk = sF + (g * 6) * NFN * BLK_E + swz8(i, e8);
             double kr[6];
 #pragma unroll
             for (int c = 0; c < 6; c++) kr[c] = pk[c * NFN * BLK_E];
-            const double *ge = geo + el * BLK_GEO;
+            const double *ge = geo + el * GST;
             const double ie = ge[23], im = ge[24], se = ge[25];
             const int off = ((g * Np + i) * BLK_E + e8) * 6;
             const double2 *pu = reinterpret_cast<const double2 *>(raw + off);
@@ -359,6 +393,7 @@ __global__ void __launch_bounds__(Blk<P, G>::T, G == 1 ? 2 : 1) stage_mma_kernel
             if (STORE_Z) bulk_store(A.z + (size_t)b * G * GS, sZ, BATCH_BYTES);
             bulk_commit();
         }
+        ring = ring1;
     }
     if (tid == 0) bulk_wait_all();
 }
