@@ -109,18 +109,20 @@ static KernelSet select_kernels(int dim, int p)
 
 typedef void (*MmaFn)(const MmaArgs);
 struct MmaSet { MmaFn fn[4]; int threads; size_t smem; };
-template <int P> static MmaSet mset()
+template <int P, int G> static MmaSet mset()
 {
-    using B = Blk<P, 1>;
-    return {{stage_mma_kernel<P, 1, 0>, stage_mma_kernel<P, 1, 1>, stage_mma_kernel<P, 1, 2>, stage_mma_kernel<P, 1, 3>}, B::T, B::smem_bytes};
+    using B = Blk<P, G>;
+    return {{stage_mma_kernel<P, G, 0>, stage_mma_kernel<P, G, 1>, stage_mma_kernel<P, G, 2>, stage_mma_kernel<P, G, 3>}, B::T, B::smem_bytes};
 }
-// the DMMA kernel covers tetrahedra of order 1..4 (order 5 does not fit the shared-memory tiling: generic kernel)
-static bool select_mma(int dim, int p, MmaSet &ms)
+// the DMMA kernel covers tetrahedra of order 1..4 (order 5 does not fit the shared-memory tiling: generic kernel);
+// G = element groups (of 8) per CTA batch
+static bool select_mma(int dim, int p, int G, MmaSet &ms)
 {
     if (dim != 3) return false;
-    switch (p) {
-        case 1: ms = mset<1>(); return true; case 2: ms = mset<2>(); return true;
-        case 3: ms = mset<3>(); return true; case 4: ms = mset<4>(); return true;
+    switch (p * 10 + G) {
+        case 11: ms = mset<1, 1>(); return true; case 21: ms = mset<2, 1>(); return true;
+        case 31: ms = mset<3, 1>(); return true; case 41: ms = mset<4, 1>(); return true;
+        case 32: ms = mset<3, 2>(); return true; case 22: ms = mset<2, 2>(); return true;
     }
     return false;
 }
@@ -412,10 +414,12 @@ int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
     c->identity = c->nranks == 1;
     for (int le = 0; le < H.NEloc && c->identity; le++) c->identity = H.elem_gid[le] == le;
     const char *force_v1 = std::getenv("DGTD_B200_GENERIC_KERNEL");   // diagnostics: run the generic (non-DMMA) kernel
-    c->blocked = !(force_v1 && force_v1[0] == '1') && H.ntab <= 128 && select_mma(H.dim, H.p, c->ms);
+    const char *groups = std::getenv("DGTD_B200_GROUPS");               // tuning: element groups per CTA batch
+    int G = groups ? std::atoi(groups) : 1;
+    c->blocked = !(force_v1 && force_v1[0] == '1') && H.ntab <= 128 && (select_mma(H.dim, H.p, G, c->ms) || select_mma(H.dim, H.p, G = 1, c->ms));
     if (c->blocked && c->ms.smem > (size_t)prop.sharedMemPerBlockOptin) c->blocked = false;
     if (c->blocked) {
-        c->BP = build_blocked_plan(H, 1);
+        c->BP = build_blocked_plan(H, G);
         c->Nalloc = (long long)c->BP.NEpad * H.Np;
         for (int m = 0; m < 4; m++) CU(cudaFuncSetAttribute((const void *)c->ms.fn[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ms.smem));
         int occ = 0; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)c->ms.fn[2], c->ms.threads, c->ms.smem));

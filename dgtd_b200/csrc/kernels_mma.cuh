@@ -107,7 +107,7 @@ template <int P, int G> struct Blk {
     static constexpr int nDoubles = oA + NA;
     static constexpr size_t bDesc = (size_t)nDoubles * 8;     // int [3][DS]
     static constexpr size_t bTab = bDesc + (size_t)3 * DS * 4;
-    static constexpr size_t bBar = bTab + (size_t)TABROWS * Nfp;   // 128*Nfp is a multiple of 8
+    static constexpr size_t bBar = bTab + (size_t)(TABROWS + 8) * Nfp;   // (128+8)*Nfp is a multiple of 8; rows 128.. : identity row
     static constexpr size_t smem_bytes = bBar + 4 * 8;
     static_assert(6 * KH * 8 >= GS, "yout staging must fit in the U buffer");
     static_assert(NFN >= Np, "k must fit in the head rows of its flux slice");
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(Blk<P, G>::T, G == 1 ? 2 : 1) stage_mma_kernel
 {
     using B = Blk<P, G>;
     constexpr int Np = B::Np, Nfp = B::Nfp, NFN = B::NFN, MT = B::MT, KSV = B::KSV, KH = B::KH, KSL = B::KSL;
-    constexpr int EB = B::EB, NW = B::NW, T = B::T, GS = B::GS, SL = B::SL, GST = B::GST, DS = B::DS;
+    constexpr int EB = B::EB, NW = B::NW, T = B::T, GS = B::GS, SL = B::SL, GST = B::GST, DS = B::DS, NQ = (Nfp + 1) / 2;
     constexpr uint32_t BATCH_BYTES = (uint32_t)G * GS * 8;
     constexpr bool LOAD_X = MODE == MODE_STAGE23, LOAD_Z = MODE == MODE_STAGE23 || MODE == MODE_STAGE4;
     constexpr bool STORE_Z = MODE == MODE_STAGE1 || MODE == MODE_STAGE23;
@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(Blk<P, G>::T, G == 1 ? 2 : 1) stage_mma_kernel
     double *sU = sm + B::oU, *sF = sm + B::oF, *sX = sm + B::oX, *sZ = sm + B::oZ, *sA = sm + B::oA;
     int *sDesc = reinterpret_cast<int *>(smem_raw + B::bDesc);
     uint8_t *sTab = smem_raw + B::bTab;
+    uint8_t *sIdent = sTab + B::TABROWS * Nfp;                           // 0..Nfp-1: trace slots are already in face-node order
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + B::bBar);   // [0],[1]: stage input buffers ; [2]: x/z
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(Blk<P, G>::T, G == 1 ? 2 : 1) stage_mma_kernel
         for (int i = tid; i < B::NA; i += T) sA[i] = asrc[i];
         const int nb = min(A.ntab, B::TABROWS) * Nfp;
         for (int i = tid; i < nb; i += T) sTab[i] = A.ftab[i];
+        if (tid < Nfp) sIdent[tid] = (uint8_t)tid;
     }
     if (tid == 0) {
         mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
@@ -220,69 +222,78 @@ __global__ void __launch_bounds__(Blk<P, G>::T, G == 1 ? 2 : 1) stage_mma_kernel
         cp_async_commit();
 
         // ---- face flux: jumps, boundary ghost states, TF/SF, upwind flux, pulled back to reference components -------
-        for (int item = tid; item < EB * NFN; item += T) {
+        // one thread = (element, face, pair of face nodes): the per-face geometry is set up once, the two nodes give ILP
+        for (int item = tid; item < EB * 4 * NQ; item += T) {
             const int e8 = item & 7;
             int r = item >> 3;
-            const int m = r % Nfp; r /= Nfp;
+            const int q = r % NQ; r /= NQ;
             const int f = r & 3, g = r >> 2, el = g * BLK_E + e8;
             const int2 info = fi[el * 4 + f];
             const int code = info.y;
-            const int nself = sTab[f * Nfp + m];
-            double uM[6], dU[6];
-            {
-                const double2 *pu = reinterpret_cast<const double2 *>(raw + ((g * Np + nself) * BLK_E + e8) * 6);
-                const double2 v0 = pu[0], v1 = pu[1], v2 = pu[2];
-                uM[0] = v0.x; uM[1] = v0.y; uM[2] = v1.x; uM[3] = v1.y; uM[4] = v2.x; uM[5] = v2.y;
-            }
-            double al = A.alpha;
-            if (info.x != -1) {
-                const double2 *pn;
-                if (info.x >= 0) {
-                    const int nn = sTab[((code >> FI_TAB_SHIFT) & FI_TAB_MASK) * Nfp + m];
-                    pn = reinterpret_cast<const double2 *>(raw + (((info.x >> 3) * Np + nn) * BLK_E + (info.x & 7)) * 6);
-                } else pn = reinterpret_cast<const double2 *>(tr + ((-2 - info.x) * Nfp + m) * 6);
-                const double2 v0 = pn[0], v1 = pn[1], v2 = pn[2];
-                dU[0] = v0.x - uM[0]; dU[1] = v0.y - uM[1]; dU[2] = v1.x - uM[2];
-                dU[3] = v1.y - uM[3]; dU[4] = v2.x - uM[4]; dU[5] = v2.y - uM[5];
-            } else {
+            const uint8_t *srow = sTab + f * Nfp;
+            const double *ubase = raw + (g * Np * BLK_E + e8) * 6;       // + node * 48
+            // where the exterior trace comes from: an element of this batch, a prefetched trace slot, or (boundary) the element itself
+            const uint8_t *nrow; const double *nbase; int nstride;
+            double ce = 0.0, ch = 0.0, al = A.alpha;
+            if (info.x >= 0) {
+                nrow = sTab + ((code >> FI_TAB_SHIFT) & FI_TAB_MASK) * Nfp;
+                nbase = raw + ((info.x >> 3) * Np * BLK_E + (info.x & 7)) * 6; nstride = BLK_E * 6;
+            } else if (info.x == -1) {
                 // boundary ghost states (HesthavenEvolution.cpp:275-313 with the global operator's SMA)
                 const int bc = code & FI_BC_MASK;
-                const double ce = bc == 1 ? -2.0 : bc == 3 ? -1.0 : 0.0;
-                const double ch = bc == 2 ? -2.0 : bc == 3 ? -1.0 : 0.0;
+                ce = bc == 1 ? -2.0 : bc == 3 ? -1.0 : 0.0;
+                ch = bc == 2 ? -2.0 : bc == 3 ? -1.0 : 0.0;
                 if (bc == 3) al = 1.0;
-#pragma unroll
-                for (int c = 0; c < 3; c++) { dU[c] = ce * uM[c]; dU[3 + c] = ch * uM[3 + c]; }
+                nrow = srow; nbase = ubase; nstride = BLK_E * 6;
+            } else {
+                nrow = sIdent; nbase = tr + (-2 - info.x) * Nfp * 6; nstride = 6;
             }
             const int tf = (code >> FI_TFSF_SHIFT) & FI_TFSF_MASK;
-            if (tf && inject) {
-                double inc[6];
-                planewave6(A.pw, A.tfsf_xyz + ((long long)(code >> FI_TIDX_SHIFT) * Nfp + m) * 3, A.t, inc);
-                const double sg = tf == 1 ? 1.0 : -1.0;
-#pragma unroll
-                for (int c = 0; c < 6; c++) dU[c] += sg * inc[c];
-            }
             const double *ge = geo + el * GST;
-            const double *ji = ge + 9;              // Jinv[a][d] at 3a+d
+            double ji[9];                           // Jinv[a][d] at 3a+d
+#pragma unroll
+            for (int i = 0; i < 9; i++) ji[i] = ge[9 + i];
             double gn[3];                           // outward normal * fscale = -grad lambda_f
 #pragma unroll
-            for (int d = 0; d < 3; d++) gn[d] = f == 0 ? (ji[d] + ji[3 + d]) + ji[6 + d] : -ji[3 * (f - 1) + d];
+            for (int d = 0; d < 3; d++) gn[d] = f == 0 ? (ji[d] + ji[3 + d]) + ji[6 + d] : -ge[9 + 3 * (f - 1) + d];
             const double fs = ge[18 + f];
-            const double ifs = 1.0 / fs;
-            const double gdE = (gn[0] * dU[0] + gn[1] * dU[1] + gn[2] * dU[2]) * ifs * ifs;
-            const double gdH = (gn[0] * dU[3] + gn[1] * dU[4] + gn[2] * dU[5]) * ifs * ifs;
+            const double ifs = 1.0 / fs, ifs2 = ifs * ifs;
             const double af = al * fs;
-            double fl[6];   // fscale * ( n x dH + alpha (dE - n (n.dE)) ),  fscale * ( -n x dE + alpha (dH - n (n.dH)) )
-            fl[0] = (gn[1] * dU[5] - gn[2] * dU[4]) + af * (dU[0] - gdE * gn[0]);
-            fl[1] = (gn[2] * dU[3] - gn[0] * dU[5]) + af * (dU[1] - gdE * gn[1]);
-            fl[2] = (gn[0] * dU[4] - gn[1] * dU[3]) + af * (dU[2] - gdE * gn[2]);
-            fl[3] = -(gn[1] * dU[2] - gn[2] * dU[1]) + af * (dU[3] - gdH * gn[0]);
-            fl[4] = -(gn[2] * dU[0] - gn[0] * dU[2]) + af * (dU[4] - gdH * gn[1]);
-            fl[5] = -(gn[0] * dU[1] - gn[1] * dU[0]) + af * (dU[5] - gdH * gn[2]);
-            double *pf = sF + (g * 6) * NFN * BLK_E + swz8(f * Nfp + m, e8);
 #pragma unroll
-            for (int a = 0; a < 3; a++) {
-                pf[a * NFN * BLK_E] = fma(ji[3 * a], fl[0], fma(ji[3 * a + 1], fl[1], ji[3 * a + 2] * fl[2]));
-                pf[(3 + a) * NFN * BLK_E] = fma(ji[3 * a], fl[3], fma(ji[3 * a + 1], fl[4], ji[3 * a + 2] * fl[5]));
+            for (int h = 0; h < 2; h++) {
+                const int m = 2 * q + h;
+                if (m >= Nfp) break;
+                double uM[6], dU[6];
+                {
+                    const double2 *pu = reinterpret_cast<const double2 *>(ubase + srow[m] * (BLK_E * 6));
+                    const double2 *pn = reinterpret_cast<const double2 *>(nbase + nrow[m] * nstride);
+                    const double2 v0 = pu[0], v1 = pu[1], v2 = pu[2], w0 = pn[0], w1 = pn[1], w2 = pn[2];
+                    uM[0] = v0.x; uM[1] = v0.y; uM[2] = v1.x; uM[3] = v1.y; uM[4] = v2.x; uM[5] = v2.y;
+                    dU[0] = fma(ce, uM[0], w0.x - uM[0]); dU[1] = fma(ce, uM[1], w0.y - uM[1]); dU[2] = fma(ce, uM[2], w1.x - uM[2]);
+                    dU[3] = fma(ch, uM[3], w1.y - uM[3]); dU[4] = fma(ch, uM[4], w2.x - uM[4]); dU[5] = fma(ch, uM[5], w2.y - uM[5]);
+                }
+                if (tf && inject) {
+                    double inc[6];
+                    planewave6(A.pw, A.tfsf_xyz + ((long long)(code >> FI_TIDX_SHIFT) * Nfp + m) * 3, A.t, inc);
+                    const double sg = tf == 1 ? 1.0 : -1.0;
+#pragma unroll
+                    for (int c = 0; c < 6; c++) dU[c] += sg * inc[c];
+                }
+                const double gdE = (gn[0] * dU[0] + gn[1] * dU[1] + gn[2] * dU[2]) * ifs2;
+                const double gdH = (gn[0] * dU[3] + gn[1] * dU[4] + gn[2] * dU[5]) * ifs2;
+                double fl[6];   // fscale * ( n x dH + alpha (dE - n (n.dE)) ),  fscale * ( -n x dE + alpha (dH - n (n.dH)) )
+                fl[0] = (gn[1] * dU[5] - gn[2] * dU[4]) + af * (dU[0] - gdE * gn[0]);
+                fl[1] = (gn[2] * dU[3] - gn[0] * dU[5]) + af * (dU[1] - gdE * gn[1]);
+                fl[2] = (gn[0] * dU[4] - gn[1] * dU[3]) + af * (dU[2] - gdE * gn[2]);
+                fl[3] = -(gn[1] * dU[2] - gn[2] * dU[1]) + af * (dU[3] - gdH * gn[0]);
+                fl[4] = -(gn[2] * dU[0] - gn[0] * dU[2]) + af * (dU[4] - gdH * gn[1]);
+                fl[5] = -(gn[0] * dU[1] - gn[1] * dU[0]) + af * (dU[5] - gdH * gn[2]);
+                double *pf = sF + (g * 6) * NFN * BLK_E + swz8(f * Nfp + m, e8);
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    pf[a * NFN * BLK_E] = fma(ji[3 * a], fl[0], fma(ji[3 * a + 1], fl[1], ji[3 * a + 2] * fl[2]));
+                    pf[(3 + a) * NFN * BLK_E] = fma(ji[3 * a], fl[3], fma(ji[3 * a + 1], fl[4], ji[3 * a + 2] * fl[5]));
+                }
             }
         }
         // ---- covariant field  u~ = J^T u / det J  (E stored negated: it only feeds dH/dt = -curl E) ----------------
