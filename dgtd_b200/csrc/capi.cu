@@ -643,6 +643,16 @@ int dgtd_setup_query(const dgtd_mesh *mesh, const dgtd_options *o, const char *n
     else if (n == "peers") { for (auto &p : H.peers) { dims.push_back(p.rank); dims.push_back(p.nfaces); dims.push_back(p.send_off); } src = dims.data(); bytes = dims.size() * 4; }
     else if (n == "dims") { dims = {H.dim, H.p, H.Np, H.Nfp, H.nf, H.NEloc, H.ntab, H.n_tfsf_faces, H.n_halo_faces}; src = dims.data(); bytes = dims.size() * 4; }
     else if (n == "node_coords") { node_coords(mesh->m, H.ref, xyz); src = xyz.data(); bytes = xyz.size() * 8; }
+    else if (n.rfind("blk_", 0) == 0) {   // tables of the DMMA kernel's plan (tetrahedra), one group per batch
+        static thread_local BlockedPlan BP;
+        BP = build_blocked_plan(H, 1);
+        if (n == "blk_dims") { dims = {BP.G, BP.ngroups, BP.nbatch, BP.NEpad, BP.slots, BP.MT, BP.KSV, BP.KSL, BP.desc_stride}; src = dims.data(); bytes = dims.size() * 4; }
+        else if (n == "blk_geo") { src = BP.geo.data(); bytes = BP.geo.size() * 8; }
+        else if (n == "blk_desc") { src = BP.desc.data(); bytes = BP.desc.size() * 4; }
+        else if (n == "blk_afrag") { src = BP.afrag.data(); bytes = BP.afrag.size() * 8; }
+        else if (n == "blk_send_off") { src = BP.send_off.data(); bytes = BP.send_off.size() * 8; }
+        else throw Error(DGTD_ERR_ARG, "unknown setup table " + n);
+    }
     else throw Error(DGTD_ERR_ARG, "unknown setup table " + n);
     *size_bytes = (long long)bytes;
     if (buf) { if ((long long)bytes > cap_bytes) throw Error(DGTD_ERR_ARG, "buffer too small"); if (bytes) std::memcpy(buf, src, bytes); }

@@ -116,7 +116,9 @@ int  dgtd_get_state(dgtd_ctx *, double *host_6N);
 /* the same with LOCAL host vectors [6][n_local] in this rank's element order (dgtd_local_elements)  */
 int  dgtd_set_state_local(dgtd_ctx *, const double *host_6nlocal);
 int  dgtd_get_state_local(dgtd_ctx *, double *host_6nlocal);
-/* device-resident state of this rank: [6][n_local] doubles (local element order)                  */
+/* device-resident state of this rank in the kernels' NATIVE layout: tetrahedra of order <= 4 use the blocked layout
+ * (groups of 8 local elements, [node][element in group][6 components], padded to whole groups); everything else
+ * [6][n_local].  Use dgtd_get_state_local / dgtd_mult(on_device=1) for layout-independent access.               */
 int  dgtd_state_device_ptr(dgtd_ctx *, double **dev);
 
 /* TimeDependentOperator::Mult at time t (SetTime + Mult).  Host pointers: global [6N] vectors,
@@ -144,7 +146,8 @@ int  dgtd_halo_bytes(const dgtd_ctx *, long long *bytes);
 
 /* Host-only diagnostic (no CUDA, no compute): copies one of the flat tables a rank would upload — "dims", "D", "lift",
  * "nodes", "fnodes", "geo", "finfo", "ftab", "elem_gid", "tfsf_xyz", "gate_xyz", "tfsf_side", "send_node", "peers",
- * "node_coords" — so that tests can check the setup against the oracle without a GPU.                            */
+ * "node_coords", and for tetrahedra the plan of the tensor-core kernel "blk_dims", "blk_geo", "blk_desc", "blk_afrag",
+ * "blk_send_off" — so that tests can check the setup against the oracle without a GPU.                            */
 int  dgtd_setup_query(const dgtd_mesh *, const dgtd_options *, const char *name, void *buf, long long cap_bytes, long long *size_bytes);
 
 const char *dgtd_last_error(void);

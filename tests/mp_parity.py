@@ -1,0 +1,71 @@
+#!/usr/bin/env python3
+"""Multi-GPU parity worker, one rank per GPU (launched by tests/test_gpu_multirank.py through torch.distributed.run).
+
+Mirror of the reference's Scaling2D test (test/mfem/mpi_FiniteElementSpaceTest.cpp:171-244): the partitioned operator
+applied to [local ; halo] must reproduce the single-rank result on every rank's owned dofs.  Here: Mult and three fused
+RK4 steps on the rank's partition (halo traces exchanged with NCCL) against the committed reference vectors (golden
+fixtures, produced by the reference-based oracle) and against a single-rank run of the same library.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import dgtd_b200 as dg
+    from conftest import load_golden, product_mesh_and_kwargs, rel_l2
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(dg.Evolution.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    uid = bytes(idt.cpu().numpy().tobytes())
+    worst = 0.0
+    for name in sys.argv[1:] or ["box3d_p3_pec_upwind", "tfsf3d_p2_on", "box3d_p2_materials", "box3d_p4_sma_partial"]:
+        pb, dat = load_golden(name)
+        meta = dat["meta"]
+        mesh, kw = product_mesh_and_kwargs(pb)
+        ev = dg.Evolution(mesh, device=local, rank=rank, nranks=world, **kw)
+        ev.comm_init(uid)
+        N, Np = ev.N, ev.Np
+        mine = np.zeros(N, bool)
+        for e in ev.local_elements():
+            mine[e * Np:(e + 1) * Np] = True
+        mask = np.tile(mine, 6)
+        ev.SetTime(meta["t0"])
+        k = ev.Mult(dat["x0_f64"])
+        e_mult = rel_l2(k[mask], dat["k0_f64"][mask])
+        ev.set_state(dat["x0_f64"])
+        ev.run(meta["t0"], meta["dt"], meta["steps"])
+        x = ev.get_state(np.zeros(6 * N))
+        e_run = rel_l2(x[mask], dat["x_final_f64"][mask])
+        # owned entries of all ranks together must tile the global vector exactly once
+        cnt = torch.tensor(mine.astype(np.int32), device="cuda")
+        dist.all_reduce(cnt)
+        assert int(cnt.min()) == 1 and int(cnt.max()) == 1, "partition does not tile the mesh"
+        assert ev.halo_bytes() > 0, "no halo faces: the case does not exercise the exchange"
+        err = torch.tensor([e_mult, e_run], dtype=torch.float64, device="cuda")
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(f"mp_parity {name}: world {world}, Mult rel-L2 {err[0].item():.2e}, run rel-L2 {err[1].item():.2e}, halo bytes/rhs {ev.halo_bytes()}")
+        worst = max(worst, float(err.max().item()))
+        ev.close()
+    dist.destroy_process_group()
+    if worst > 1e-12:
+        raise SystemExit(f"multi-rank parity failed: {worst:.3e}")
+    if rank == 0:
+        print("MP_PARITY_OK")
+
+
+if __name__ == "__main__":
+    main()

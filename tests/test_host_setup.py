@@ -1,0 +1,171 @@
+"""CPU-only checks of the product's host side: the C ABI loads and exports what include/dgtd_b200.h declares, and the
+flat tables a rank uploads (reference element, geometry, vmapP, boundary codes, TF/SF sides, tensor-core plan, halo plan)
+agree with the oracle, which is pinned to the reference (tests/test_oracle.py).  No compute entry point is called."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import dgtd_b200 as dg
+from conftest import ROOT, golden_cases, load_golden, product_mesh_and_kwargs
+from oracle.dgtd_oracle import HesthavenOracle
+
+FI_TAB = lambda code: (code >> 4) & 0xff
+
+
+def test_library_exports_every_declared_symbol():
+    assert len(dg.HEADER_SYMBOLS) >= 30
+    for s in dg.HEADER_SYMBOLS:
+        assert hasattr(dg.lib, s), s
+    assert b"sm_100a" in dg.lib.dgtd_version()
+
+
+def test_compute_entry_points_fail_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    pb, _ = load_golden("box3d_p1_gauss")
+    mesh, kw = product_mesh_and_kwargs(pb)
+    with pytest.raises(dg.DgtdError) as ei:
+        dg.Evolution(mesh, **kw)
+    assert ei.value.code == -2 and "no CPU fallback" in str(ei.value)
+
+
+def _q(mesh, kw, name, dtype, **extra):
+    k = dict(kw); k.update(extra)
+    return dg.setup_query(mesh, name, dtype, **k)
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_setup_tables_match_the_oracle(name):
+    pb, dat = load_golden(name)
+    O = HesthavenOracle(pb)
+    mesh, kw = product_mesh_and_kwargs(pb)
+    dim, p, Np, Nfp, nf, NE = (int(v) for v in _q(mesh, kw, "dims", np.int32)[:6])
+    assert (dim, p, Np, Nfp, nf, NE) == (O.dim, pb.order, O.Np, O.Nfp, O.nf, O.NE)
+    # (the product derives its operators in long double, the oracle in double: compare relative to the largest entry)
+    assert np.abs(_q(mesh, kw, "D", np.float64).reshape(dim, Np, Np) - O.ref.D).max() < 5e-12 * np.abs(O.ref.D).max()
+    assert np.abs(_q(mesh, kw, "lift", np.float64).reshape(nf, Np, Nfp) - O.ref.lift).max() < 5e-12 * np.abs(O.ref.lift).max()
+    assert np.array_equal(_q(mesh, kw, "fnodes", np.int32).reshape(nf, Nfp), O.ref.fnodes)
+    assert np.abs(_q(mesh, kw, "node_coords", np.float64).reshape(NE, Np, 3) - O.xyz).max() < 1e-14
+    gid = _q(mesh, kw, "elem_gid", np.int32)
+    assert sorted(gid) == list(range(NE))                      # a permutation (Morton order in 3-D)
+    geo = _q(mesh, kw, "geo", np.float64).reshape(NE, 16)
+    assert np.abs(geo[:, :9].reshape(NE, 3, 3) - O.Jinv[gid]).max() < 1e-12 * max(1.0, np.abs(O.Jinv).max())
+    assert np.abs(geo[:, 9:9 + nf] - O.fscale[gid]).max() < 1e-12 * O.fscale.max()
+    assert np.allclose(geo[:, 13], O.inv_eps[gid]) and np.allclose(geo[:, 14], O.inv_mu[gid]) and np.allclose(geo[:, 15], O.sig_eps[gid])
+    # vmapP: the neighbour node named by (finfo, ftab) is the oracle's vmapP (and sits at the same point in space)
+    finfo = _q(mesh, kw, "finfo", np.int32).reshape(NE, 4, 2)
+    ftab = _q(mesh, kw, "ftab", np.uint8).reshape(-1, Nfp)
+    l2g = gid
+    for le in range(NE):
+        e = l2g[le]
+        for f in range(nf):
+            nb, code = finfo[le, f]
+            if O.nbr[e, f] < 0:
+                assert nb == -1 and (code & 3) == O.bc[e, f]
+                continue
+            assert l2g[nb] == O.nbr[e, f]
+            assert np.array_equal(l2g[nb] * Np + ftab[FI_TAB(code)], O.vmapP[e, f])
+            tf = (code >> 2) & 3
+            assert tf == {0: 0, 1: 1, -1: 2}[int(O.tfsf_face[e, f])]
+    assert np.array_equal(_q(mesh, kw, "tfsf_side", np.int32), O.tfsf_side[gid])
+
+
+@pytest.mark.parametrize("name", [n for n in golden_cases() if "3d" in n])
+def test_tensor_core_plan_is_consistent(name):
+    """The blocked plan re-expresses finfo per batch (in-batch neighbour / boundary / trace slot): decode it back."""
+    pb, _ = load_golden(name)
+    O = HesthavenOracle(pb)
+    mesh, kw = product_mesh_and_kwargs(pb)
+    Np, Nfp, NE = O.Np, O.Nfp, O.NE
+    G, ngroups, nbatch, NEpad, slots, MT, KSV, KSL, DS = (int(v) for v in _q(mesh, kw, "blk_dims", np.int32))
+    assert NEpad % 8 == 0 and NEpad >= NE and nbatch * 8 * G == NEpad and DS % 4 == 0
+    finfo = _q(mesh, kw, "finfo", np.int32).reshape(NE, 4, 2)
+    desc = _q(mesh, kw, "blk_desc", np.int32).reshape(nbatch, DS)
+    EB = 8 * G
+    for b in range(nbatch):
+        fi = desc[b, :EB * 8].reshape(EB, 4, 2)
+        td = desc[b, EB * 8:EB * 8 + slots * 2].reshape(slots, 2)
+        used = desc[b, EB * 8 + slots * 2]
+        seen = set()
+        for le in range(EB):
+            e = b * EB + le
+            for f in range(4):
+                x, code = fi[le, f]
+                if e >= NE:
+                    assert x == -1 and (code & 0xf) == 0
+                    continue
+                nb, code1 = finfo[e, f]
+                assert code == code1
+                if nb == -1:
+                    assert x == -1
+                elif x >= 0:
+                    assert b * EB + x == nb
+                else:
+                    s = -2 - x
+                    assert 0 <= s < used and s not in seen
+                    seen.add(s)
+                    assert td[s, 0] == nb and td[s, 1] == FI_TAB(code)
+        assert len(seen) == used
+    # geometry records: J * Jinv = I, 1/det
+    geo = _q(mesh, kw, "blk_geo", np.float64).reshape(NEpad, 32)
+    J, Ji = geo[:, :9].reshape(-1, 3, 3), geo[:, 9:18].reshape(-1, 3, 3)
+    assert np.abs(np.einsum("eda,eac->edc", J, Ji) - np.eye(3)).max() < 1e-12
+    assert np.allclose(geo[:NE, 22] * np.linalg.det(J[:NE]), 1.0, rtol=1e-13)
+    # A fragments reproduce D and LIFT/2 (lane l holds A[l>>2][l&3])
+    af = _q(mesh, kw, "blk_afrag", np.float64)
+    Dm = _q(mesh, kw, "D", np.float64).reshape(3, Np, Np)
+    L = _q(mesh, kw, "lift", np.float64).reshape(4, Np, Nfp)
+    Lfull = np.concatenate([L[f] for f in range(4)], axis=1)      # (Np, 4*Nfp)
+    av = af[:3 * MT * KSV * 32].reshape(3, MT, KSV, 8, 4)
+    al = af[3 * MT * KSV * 32:].reshape(MT, KSL, 8, 4)
+    Dr = np.zeros((3, MT * 8, KSV * 4)); Dr[:, :Np, :Np] = Dm
+    Lr = np.zeros((MT * 8, KSL * 4)); Lr[:Np, :4 * Nfp] = 0.5 * Lfull
+    assert np.array_equal(av.transpose(0, 1, 3, 2, 4).reshape(3, MT * 8, KSV * 4), Dr)
+    assert np.array_equal(al.transpose(0, 2, 1, 3).reshape(MT * 8, KSL * 4), Lr)
+
+
+def test_partitioner_and_halo_plan_two_ranks_in_process():
+    """Both sides of every shared face enumerate it identically and ship the nodes the receiver expects."""
+    pb, _ = load_golden("box3d_p3_pec_upwind")
+    O = HesthavenOracle(pb)
+    mesh, kw = product_mesh_and_kwargs(pb)
+    part = mesh.partition(2)
+    assert set(part) == {0, 1} and abs(int((part == 0).sum()) - int((part == 1).sum())) <= 1
+    Np, Nfp = O.Np, O.Nfp
+    plan = {}
+    for r in range(2):
+        gid = _q(mesh, kw, "elem_gid", np.int32, rank=r, nranks=2)
+        assert np.array_equal(np.sort(gid), np.nonzero(part == r)[0])
+        send = _q(mesh, kw, "send_node", np.int32, rank=r, nranks=2).reshape(-1, Nfp)
+        finfo = _q(mesh, kw, "finfo", np.int32, rank=r, nranks=2).reshape(len(gid), 4, 2)
+        peers = _q(mesh, kw, "peers", np.int32, rank=r, nranks=2).reshape(-1, 3)
+        assert len(peers) == 1 and peers[0, 0] == 1 - r and peers[0, 1] == len(send)
+        plan[r] = (gid, send, finfo)
+    assert len(plan[0][1]) == len(plan[1][1]) > 0
+    xyz = O.xyz.reshape(-1, 3)
+    for r in range(2):
+        gid, send, finfo = plan[r]
+        ogid, osend, _ = plan[1 - r]
+        # what the peer sends into my halo slot s must be the points of my face nodes, in my face-node order
+        for le in range(len(gid)):
+            for f in range(4):
+                nb, code = finfo[le, f]
+                if nb <= -2:
+                    s = -2 - nb
+                    mine = xyz[gid[le] * Np + O.ref.fnodes[f]]
+                    theirs = xyz[ogid[osend[s] // Np] * Np + osend[s] % Np]
+                    assert np.abs(mine - theirs).max() < 1e-14
+
+
+def test_halo_plan_world_size_2_gloo():
+    """The same through two processes that exchange their send lists' coordinates over gloo (host logic of the N>1 path)."""
+    script = os.path.join(ROOT, "tests", "mp_halo_plan_cpu.py")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29431", script]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert r.returncode == 0 and r.stdout.count("HALO_PLAN_OK") == 2, r.stdout[-2000:] + r.stderr[-2000:]
