@@ -46,6 +46,18 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel_info, dofs):
+    """dram__bytes_read.sum + dram__bytes_write.sum per stage launch from the committed `ncu --set full` capture of this
+    kernel on this workload (profiles/traffic.json, written from the .ncu-rep by hand); None when there is no capture."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    for rec in json.load(open(p)):
+        if kernel_info.startswith(rec["kernel_prefix"]) and rec["dofs_per_gpu"] == dofs:
+            return rec["dram_bytes_per_launch"]
+    return None
+
+
 class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -240,8 +252,9 @@ def main():
                            "l2": "inputs (4 x %.0f MB per GPU) are larger than L2, no flush" % (6 * nloc * 8 / 1e6),
                            "halo_bytes_per_rhs": ev.halo_bytes(), "state_norm": float(norm2.sqrt().item())},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                             "traffic": None, "peak_source": how, "alg_bytes_per_dof_update": B_ALG[ORDER],
-                             "kernel": "stage_kernel<3,3,*>", "avg_launch_ms": launch_ms},
+                             "traffic": ncu_traffic(ev.kernel_info(), 6 * nloc), "peak_source": how,
+                             "alg_bytes_per_dof_update": B_ALG[ORDER], "alg_bytes_per_launch": alg_bytes,
+                             "kernel": ev.kernel_info(), "avg_launch_ms": launch_ms},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 6 * nloc * 8 * n_gpus, "d2h_bytes_per_step": 6 * nloc * 8 * n_gpus,
                         "steps": e2e_steps, "how": "dgtd_set_state_local(host) + dgtd_rk4_step + dgtd_get_state_local(host) per step, pinned host memory"},
                 "gpu_launches": int(launches),

@@ -58,6 +58,7 @@ def _load():
     L.dgtd_version.restype = C.c_char_p
     L.dgtd_launch_count.restype = C.c_longlong
     L.dgtd_launch_count.argtypes = [C.c_void_p]
+    L.dgtd_kernel_info.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.dgtd_mesh_destroy.restype = None
     L.dgtd_mesh_destroy.argtypes = [C.c_void_p]
     L.dgtd_destroy.restype = None
@@ -275,6 +276,11 @@ class Evolution:
 
     def launch_count(self):
         return lib.dgtd_launch_count(self._h)
+
+    def kernel_info(self):
+        buf = C.create_string_buffer(256)
+        _ck(lib.dgtd_kernel_info(self._h, buf, 256))
+        return buf.value.decode()
 
     def halo_bytes(self):
         b = C.c_longlong()

@@ -11,6 +11,7 @@
 
 #include <dlfcn.h>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -616,6 +617,18 @@ int dgtd_synchronize(dgtd_ctx *c)
     GUARD_END
 }
 long long dgtd_launch_count(const dgtd_ctx *c) { return c ? c->launches : 0; }
+int dgtd_kernel_info(const dgtd_ctx *c, char *buf, int cap)
+{
+    if (!c || !buf || cap < 1) return fail(DGTD_ERR_ARG, "bad argument");
+    char tmp[256];
+    if (c->blocked)
+        std::snprintf(tmp, sizeof tmp, "stage_mma_kernel<P=%d,G=%d,MODE> DMMA m8n8k4, blocked layout, %d threads, %zu B smem, grid %d",
+                      c->H.p, c->BP.G, c->ms.threads, c->ms.smem, c->grid);
+    else
+        std::snprintf(tmp, sizeof tmp, "stage_kernel<DIM=%d,P=%d,MODE> generic, %d threads, %zu B smem, grid %d", c->H.dim, c->H.p, c->ks.threads, c->ks.smem, c->grid);
+    std::snprintf(buf, (size_t)cap, "%s", tmp);
+    return DGTD_OK;
+}
 
 // Host-only diagnostic: the flat operator tables a rank would upload (no CUDA involved, no compute).
 int dgtd_setup_query(const dgtd_mesh *mesh, const dgtd_options *o, const char *name, void *buf, long long cap_bytes, long long *size_bytes)

@@ -137,6 +137,8 @@ int  dgtd_sample(dgtd_ctx *, int npts, const int *local_elem, const double *shap
 int  dgtd_synchronize(dgtd_ctx *);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches)               */
 long long dgtd_launch_count(const dgtd_ctx *);
+/* which stage kernel this context runs (name, tiling, launch shape) — for benchmark reports                */
+int  dgtd_kernel_info(const dgtd_ctx *, char *buf, int cap);
 
 /* ---- multi-GPU halo exchange (one context per rank/GPU, NCCL over NVLink) ----------------------- */
 int  dgtd_comm_unique_id(void *id128);                    /* rank 0: ncclGetUniqueId              */

@@ -849,6 +849,70 @@ static int cmdKnown(const std::string &path, const std::string &meshFile)
    return (bad || n == 0) ? 1 : 0;
 }
 
+#ifdef DGTD_WITH_B200_SHELL
+// ----------------------------------------------------------------------------
+// `shell`: the product's drop-in shells (dgtd_b200/mfem_shell/B200Evolution.h) driven exactly like the reference drives
+// its own operator — mfem::TimeDependentOperator::Mult, mfem::RK4Solver::Step — next to the reference-based GlobalOracle
+// on the same mfem::FiniteElementSpace.  Needs a GPU (the product has no CPU path); this binary is the checker.
+// ----------------------------------------------------------------------------
+#include "B200Evolution.h"
+static double relL2(const Vector &a, const Vector &b)
+{
+   Vector d(a); d -= b; double nb = b.Norml2(); return d.Norml2() / (nb > 0 ? nb : 1.0);
+}
+static int cmdShell(std::map<std::string, std::string> &a)
+{
+   Problem pd = problemFromArgs(a);
+   Mesh &mesh = *pd.mesh; const int dim = mesh.Dimension();
+   DG_FECollection fec(pd.order, dim, BasisType::GaussLobatto);
+   FiniteElementSpace fes(&mesh, &fec);
+   const int N = fes.GetNDofs();
+   Factory F(pd, fes);
+   GlobalOracle op(N);
+   op.A = buildGlobal(F);
+   std::vector<double> xyz; nodeCoords(fes, xyz);
+   op.pw = pd.pw;
+   if (!pd.tfsf_tags.empty()) { op.Atfsf = buildTFSF(F); op.src = buildTFSFSource(F, xyz); }
+   maxwell::B200Problem bp;
+   bp.order = pd.order; bp.alpha = pd.alpha;
+   for (auto &kv : pd.bdr) { bp.bdr[kv.first] = kv.second == BC_PEC ? DGTD_BC_PEC : kv.second == BC_PMC ? DGTD_BC_PMC : DGTD_BC_SMA; }
+   bp.tfsfTags = pd.tfsf_tags; bp.materials = pd.mat;
+   if (pd.pw.on)
+   {
+      bp.planewave.enabled = 1; bp.planewave.spread = pd.pw.spread; bp.planewave.mean1d = pd.pw.mean1d; bp.planewave.freq = pd.pw.freq;
+      for (int d = 0; d < 3; d++) { bp.planewave.pol[d] = pd.pw.pol[d]; bp.planewave.dir[d] = pd.pw.dir[d]; }
+      bp.planewave.fieldtype = pd.pw.fieldtype;
+   }
+   maxwell::B200Evolution ev(fes, bp);
+   const double dt = a.count("dt") ? std::stod(a["dt"]) : 1e-3;
+   const int steps = a.count("steps") ? std::stoi(a["steps"]) : 3;
+   const double t0 = a.count("t0") ? std::stod(a["t0"]) : 0.0;
+   Vector x0; initState(x0, a.count("init") ? a["init"] : "random:1", xyz, N, dim);
+   // (1) TimeDependentOperator::Mult
+   Vector kr, kb;                               // kb arrives unsized, as in GlobalEvolution.cpp:807-810
+   op.SetTime(t0); op.Mult(x0, kr); ev.SetTime(t0); ev.Mult(x0, kb);
+   const double eMult = relL2(kb, kr);
+   // (2) mfem::RK4Solver driving each operator (Solver.cpp:41-47, 124-125, 544)
+   Vector xr(x0), xm(x0), xf(x0);
+   { RK4Solver rk; rk.Init(op); double t = t0; for (int s = 0; s < steps; s++) { double d = dt; rk.Step(xr, t, d); } }
+   { RK4Solver rk; rk.Init(ev); double t = t0; for (int s = 0; s < steps; s++) { double d = dt; rk.Step(xm, t, d); } }
+   // (3) the fused B200RK4Solver in RK4Solver's place, and its device-resident loop
+   { maxwell::B200RK4Solver rk; rk.Init(ev); double t = t0; for (int s = 0; s < steps; s++) { double d = dt; rk.Step(xf, t, d); } }
+   Vector xres(x0);
+   { maxwell::B200RK4Solver rk; rk.Init(ev); double t = t0; rk.Upload(xres); rk.Run(t, dt, steps); rk.Download(xres); }
+   const double eRk = relL2(xm, xr), eFused = relL2(xf, xr), eRes = relL2(xres, xr);
+   // (4) a foreign operator through B200RK4Solver must reproduce RK4Solver bit for bit
+   Vector xg(x0);
+   { maxwell::B200RK4Solver rk; rk.Init(op); double t = t0; for (int s = 0; s < steps; s++) { double d = dt; rk.Step(xg, t, d); } }
+   const double eGen = relL2(xg, xr);
+   printf("{\"n\": %d, \"steps\": %d, \"mult_rel_l2\": %.3e, \"mfem_rk4_on_b200_rel_l2\": %.3e, \"fused_rk4_rel_l2\": %.3e, "
+          "\"resident_run_rel_l2\": %.3e, \"generic_fallback_rel_l2\": %.3e, \"tfsf_applied\": %ld, \"tfsf_skipped\": %ld}\n",
+          N, steps, eMult, eRk, eFused, eRes, eGen, op.napplied, op.nskipped);
+   const double tol = 1e-10;                    // north_star: 1e-10 relative L2 per step
+   return (eMult < tol && eRk < tol && eFused < tol && eRes < tol && eGen == 0.0) ? 0 : 1;
+}
+#endif
+
 int main(int argc, char **argv)
 {
    if (argc < 2)
@@ -865,6 +929,9 @@ int main(int argc, char **argv)
    auto a = parseArgs(argc, argv, 2);
    if (cmd == "gen") { return cmdGen(a, false); }
    if (cmd == "bench") { return cmdGen(a, true); }
+#ifdef DGTD_WITH_B200_SHELL
+   if (cmd == "shell") { return cmdShell(a); }
+#endif
    fprintf(stderr, "unknown command %s\n", cmd.c_str());
    return 2;
 }
