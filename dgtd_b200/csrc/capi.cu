@@ -8,6 +8,7 @@
 #include "host.hpp"
 #include "kernels.cuh"
 #include "kernels_mma.cuh"
+#include "kernels_ws.cuh"
 
 #include <dlfcn.h>
 #include <cmath>
@@ -128,10 +129,25 @@ static bool select_mma(int dim, int p, int G, MmaSet &ms)
     return false;
 }
 
+// the warp-specialised kernel: tetrahedra of order 2..3 without conductivity, 16-element batches, one CTA per SM
+template <int P> static MmaSet wsset()
+{
+    using B = Ws<P>;
+    return {{stage_ws_kernel<P, 0>, stage_ws_kernel<P, 1>, stage_ws_kernel<P, 2>, stage_ws_kernel<P, 3>}, B::T, B::smem_bytes};
+}
+static bool select_ws(int dim, int p, MmaSet &ms)
+{
+    if (dim != 3) return false;
+    if (p == 3) { ms = wsset<3>(); return true; }
+    if (p == 2) { ms = wsset<2>(); return true; }
+    return false;
+}
+
 struct dgtd_ctx {
     HostOp H;
     BlockedPlan BP;
     bool blocked = false;            // state lives in the blocked layout and the DMMA stage kernel runs
+    bool ws = false;                 // ... its warp-specialised variant
     bool identity = true;            // local element order == global order (single rank, no reordering)
     long long Nalloc = 0;            // scalar dofs allocated per component (padded to whole batches when blocked)
     MmaSet ms{};
@@ -414,18 +430,25 @@ int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
     c->Nloc = (long long)H.NEloc * H.Np; c->Nglob = H.NEglob * H.Np;
     c->identity = c->nranks == 1;
     for (int le = 0; le < H.NEloc && c->identity; le++) c->identity = H.elem_gid[le] == le;
-    const char *force_v1 = std::getenv("DGTD_B200_GENERIC_KERNEL");   // diagnostics: run the generic (non-DMMA) kernel
-    const char *groups = std::getenv("DGTD_B200_GROUPS");               // tuning: element groups per CTA batch
+    // kernel choice: DGTD_B200_KERNEL = ws | mma | generic overrides the default (the fastest eligible one)
+    const char *kenv = std::getenv("DGTD_B200_KERNEL");
+    const std::string ksel = kenv ? kenv : "";
+    const char *groups = std::getenv("DGTD_B200_GROUPS");               // tuning of the mma kernel: element groups per CTA batch
     int G = groups ? std::atoi(groups) : 1;
-    c->blocked = !(force_v1 && force_v1[0] == '1') && H.ntab <= 128 && (select_mma(H.dim, H.p, G, c->ms) || select_mma(H.dim, H.p, G = 1, c->ms));
-    if (c->blocked && c->ms.smem > (size_t)prop.sharedMemPerBlockOptin) c->blocked = false;
+    bool has_sigma = false;
+    for (int le = 0; le < H.NEloc; le++) has_sigma |= H.geo[(size_t)le * GEO_STRIDE + 15] != 0.0;
+    const bool tabs_ok = H.ntab <= 128;
+    if (ksel != "generic" && tabs_ok) {
+        if (ksel != "mma" && !has_sigma && select_ws(H.dim, H.p, c->ms) && c->ms.smem <= (size_t)prop.sharedMemPerBlockOptin) { c->blocked = c->ws = true; G = 2; }
+        else if (select_mma(H.dim, H.p, G, c->ms) || select_mma(H.dim, H.p, G = 1, c->ms)) c->blocked = c->ms.smem <= (size_t)prop.sharedMemPerBlockOptin;
+    }
     if (c->blocked) {
         c->BP = build_blocked_plan(H, G);
         c->Nalloc = (long long)c->BP.NEpad * H.Np;
         for (int m = 0; m < 4; m++) CU(cudaFuncSetAttribute((const void *)c->ms.fn[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ms.smem));
         int occ = 0; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)c->ms.fn[2], c->ms.threads, c->ms.smem));
         if (occ < 1) throw Error(DGTD_ERR_UNSUPPORTED, "DMMA stage kernel does not fit on an SM");
-        c->grid = (int)std::min<long long>(c->BP.nbatch, (long long)prop.multiProcessorCount * occ);
+        c->grid = (int)std::min<long long>(c->BP.nbatch, (long long)prop.multiProcessorCount * (c->ws ? 1 : occ));
         c->bgeo.upload(c->BP.geo); c->bafrag.upload(c->BP.afrag); c->bdesc.upload(c->BP.desc); c->bsend_off.upload(c->BP.send_off, 1);
     } else {
         c->Nalloc = c->Nloc;
@@ -622,8 +645,8 @@ int dgtd_kernel_info(const dgtd_ctx *c, char *buf, int cap)
     if (!c || !buf || cap < 1) return fail(DGTD_ERR_ARG, "bad argument");
     char tmp[256];
     if (c->blocked)
-        std::snprintf(tmp, sizeof tmp, "stage_mma_kernel<P=%d,G=%d,MODE> DMMA m8n8k4, blocked layout, %d threads, %zu B smem, grid %d",
-                      c->H.p, c->BP.G, c->ms.threads, c->ms.smem, c->grid);
+        std::snprintf(tmp, sizeof tmp, "%s<P=%d,G=%d,MODE> DMMA m8n8k4, blocked layout, %d threads, %zu B smem, grid %d",
+                      c->ws ? "stage_ws_kernel" : "stage_mma_kernel", c->H.p, c->BP.G, c->ms.threads, c->ms.smem, c->grid);
     else
         std::snprintf(tmp, sizeof tmp, "stage_kernel<DIM=%d,P=%d,MODE> generic, %d threads, %zu B smem, grid %d", c->H.dim, c->H.p, c->ks.threads, c->ks.smem, c->grid);
     std::snprintf(buf, (size_t)cap, "%s", tmp);
