@@ -1,12 +1,13 @@
-// sm_100a warp-specialised DMMA stage kernel (tetrahedra, sigma = 0): one persistent 18-warp CTA per SM.
+// sm_100a warp-specialised DMMA stage kernel (tetrahedra, sigma = 0): one persistent 20-warp CTA per SM.
 //
 // Same arithmetic and data layout as stage_mma_kernel (kernels_mma.cuh), re-organised after its ncu profile
 // (profiles/r1_v2d_stage_mma_ncu_summary.txt: 12 warps/SM, phases serialised by block barriers, LSU pipe 62 %, DMMA 36 %):
 //   warps  0..11  contraction: 6 output tile types (field, reference component) x {volume, LIFT}; each warp keeps ITS 30
 //                 DMMA A-fragments in registers for the whole kernel (no operator traffic at all) and the 12 warps
 //                 load the four SM sub-partitions evenly (3 each);
-//   warps 12..15  flux: thread = (element, face, half of the face nodes) — geometry set up once per five nodes;
-//   warps 16..17  covariant transform of batch b+1 and push-forward + Runge-Kutta stage of batch b-1,
+//   warps 12..17  flux: thread = (element, face, third of the face nodes) — geometry set up once per 3-4 nodes; the traces
+//                 of faces leaving the batch are gathered (cp.async -> mbarrier) by the LIFT contraction warps;
+//   warps 18..19  covariant transform of batch b+1 and push-forward + Runge-Kutta stage of batch b-1,
 //                 thread = (element, quarter of the nodes).
 // The roles run concurrently on different batches (16 elements each) and hand buffers over through mbarriers; the only
 // block-wide barrier is at start-up.  HBM traffic is unchanged: bulk-TMA loads of y_in / x / z, bulk-TMA stores of
@@ -30,9 +31,9 @@ template <int P> struct Ws {
     static constexpr int CAP = 3 * EB;                         // trace slots staged in shared memory; the rest is read from L2 directly
     static constexpr int DS = EB * 8 + SL * 2 + 4;
     static constexpr int TABROWS = 128, GST = BLK_GEO + 2;
-    static constexpr int NWG = 12, NWF = 4, NWR = 2, T = 32 * (NWG + NWF + NWR);
-    static constexpr int NF = 32 * NWF, NR = 32 * NWR;
-    static constexpr int NH = 2, HN = (Nfp + NH - 1) / NH;     // face halves, nodes per half
+    static constexpr int NWG = 12, NWF = 6, NWR = 2, T = 32 * (NWG + NWF + NWR);
+    static constexpr int NF = 32 * NWF, NR = 32 * NWR, NL = 32 * (NWG / 2);   // flux / transform+RK / LIFT-contraction threads
+    static constexpr int NH = 3, HN = (Nfp + NH - 1) / NH;     // parts of a face (nodes h, h+NH, ...), nodes per part
     static constexpr int NQ = NR / EB, QN = (Np + NQ - 1) / NQ;   // node quarters per element, nodes per quarter
     static constexpr int UB = G * 6 * KH * BLK_E, FB = G * 6 * NFN * BLK_E;
     static constexpr int oRaw = 0;                             // [2][BS]
@@ -50,12 +51,12 @@ template <int P> struct Ws {
     static constexpr size_t smem_bytes = bBar + NBAR * 8;
     static_assert(NFN >= 2 * Np, "both partial results must fit in a flux slice");
     static_assert(2 * MT * KSV <= 32 && MT * KSL <= 32, "A fragments must fit in registers");
-    static_assert(NF == EB * 4 * NH && NR == EB * NQ, "role thread counts are tied to the batch shape");
+    static_assert(NF == EB * 4 * NH && NR == EB * NQ && NWG == 12, "role thread counts are tied to the batch shape");
     static_assert((bDesc % 16) == 0 && (bBar % 8) == 0 && (DS % 4) == 0, "alignment");
 };
 
 // barrier slots
-enum { WB_RAW = 0, WB_DG = 2, WB_XZ = 5, WB_FULLU = 6, WB_FULLF = 8, WB_DONEK = 10, WB_FREE = 12 };
+enum { WB_RAW = 0, WB_DG = 2, WB_XZ = 5, WB_FULLU = 6, WB_FULLF = 8, WB_DONEK = 10, WB_FREE = 12, WB_TR = 14 };
 
 template <int P, int MODE>
 __global__ void __launch_bounds__(Ws<P>::T, 1) stage_ws_kernel(const MmaArgs A)
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(Ws<P>::T, 1) stage_ws_kernel(const MmaArgs A)
         mbar_init(&bars[WB_FULLF], B::NF); mbar_init(&bars[WB_FULLF + 1], B::NF);
         mbar_init(&bars[WB_DONEK], B::NWG); mbar_init(&bars[WB_DONEK + 1], B::NWG);
         mbar_init(&bars[WB_FREE], 1); mbar_init(&bars[WB_FREE + 1], 1);
+        mbar_init(&bars[WB_TR], B::NL); mbar_init(&bars[WB_TR + 1], B::NL);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
     }
@@ -108,6 +110,27 @@ __global__ void __launch_bounds__(Ws<P>::T, 1) stage_ws_kernel(const MmaArgs A)
     auto load_raw = [&](int n) {
         mbar_expect_tx(&bars[WB_RAW + (n & 1)], BATCH_BYTES);
         bulk_load(sm + B::oRaw + (n & 1) * BS, A.yin + (size_t)(b0 + n * gstep) * BS, BATCH_BYTES, &bars[WB_RAW + (n & 1)]);
+    };
+
+    // traces of faces leaving batch n -> buffer n & 1, issued by the NL threads of the LIFT contraction warps (they idle
+    // while the producers work); completion is signalled on an mbarrier by the copies themselves
+    auto issue_traces = [&](int n, int tl) {
+        mbar_wait(&bars[WB_DG + n % 3], (n / 3) & 1);
+        const int *dsc = sDesc + (n % 3) * DS;
+        const int nt = min(dsc[EB * 8 + SL * 2], CAP);
+        const int2 *td = reinterpret_cast<const int2 *>(dsc + EB * 8);
+        double *tdst = sm + B::oTr + (n & 1) * CAP * Nfp * 6;
+        constexpr int PER = Nfp * 3, LANES = B::NL / PER;      // (node, 16-byte chunk) pairs ; slots handled concurrently
+        const int mc = tl % PER, m = mc / 3, ch = mc - 3 * m;
+        if (tl < LANES * PER)
+            for (int slot = tl / PER; slot < nt; slot += LANES) {
+                const int2 d = td[slot];
+                const double *src;
+                if (d.x >= 0) src = A.yin + (((size_t)(d.x >> 3) * Np + sTab[d.y * Nfp + m]) * BLK_E + (d.x & 7)) * 6;
+                else src = A.halo + ((size_t)(-1 - d.x) * Nfp + m) * 6;
+                cp_async16(tdst + (slot * Nfp + m) * 6 + 2 * ch, src + 2 * ch);
+            }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars[WB_TR + (n & 1)])) : "memory");
     };
 
     if (warp < B::NWG) {
@@ -131,8 +154,12 @@ __global__ void __launch_bounds__(Ws<P>::T, 1) stage_ws_kernel(const MmaArgs A)
                 for (int ks = 0; ks < KSL; ks++) aF[mt * KSL + ks] = __ldg(A.afrag + 3 * MT * KSV * 32 + (mt * KSL + ks) * 32 + lane);
         }
         const int boff = (lane & 3) * BLK_E + ((lane >> 2) ^ ((lane & 2) << 1));
+        const int tl = tid - 32 * (B::NWG / 2);               // LIFT warps: index among the trace-issuing threads
+        if (part == 1) issue_traces(0, tl);
         for (int it = 0; it < nmine; it++) {
             const int par = it & 1, ph = (it >> 1) & 1;
+            // buffer (it+1)&1 was last read by the flux of batch it-1, which this warp's previous contraction waited for
+            if (part == 1 && it + 1 < nmine) issue_traces(it + 1, tl);
             const double *sU = sm + B::oU + par * B::UB;
             double *sF = sm + B::oF + par * B::FB;
             mbar_wait(&bars[(part == 0 ? WB_FULLU : WB_FULLF) + par], ph);
@@ -178,37 +205,15 @@ __global__ void __launch_bounds__(Ws<P>::T, 1) stage_ws_kernel(const MmaArgs A)
     } else if (warp < B::NWG + B::NWF) {
         // =============================== flux warps ===========================================================
         const int t = tid - 32 * B::NWG;                      // 0..NF-1
-        const int e8 = t & 7, h = (t >> 3) & 1, f = (t >> 4) & 3, g = t >> 6, el = g * BLK_E + e8;
+        const int e8 = t & 7, h = (t >> 3) % B::NH, f = ((t >> 3) / B::NH) & 3, g = (t >> 3) / (4 * B::NH), el = g * BLK_E + e8;
         const bool inject = A.pw_on && (A.gate == nullptr || *A.gate >= 1e-16);
         if (t == 0) {   // start-up loads of the whole CTA
             for (int n = 0; n < 3 && n < nmine; n++) load_desc_geo(n);
             for (int n = 0; n < 2 && n < nmine; n++) load_raw(n);
         }
-        auto issue_traces = [&](int n) {                       // traces of batch n into buffer n & 1 (descriptors must have landed)
-            const int *dsc = sDesc + (n % 3) * DS;
-            const int nt = min(dsc[EB * 8 + SL * 2], CAP);
-            const int2 *td = reinterpret_cast<const int2 *>(dsc + EB * 8);
-            double *tdst = sm + B::oTr + (n & 1) * CAP * Nfp * 6;
-            for (int i = t; i < nt * Nfp * 3; i += B::NF) {
-                const int slot = i / (Nfp * 3), r = i - slot * (Nfp * 3), m = r / 3, ch = r - 3 * m;
-                const int2 d = td[slot];
-                const double *src;
-                if (d.x >= 0) src = A.yin + (((size_t)(d.x >> 3) * Np + sTab[d.y * Nfp + m]) * BLK_E + (d.x & 7)) * 6;
-                else src = A.halo + ((size_t)(-1 - d.x) * Nfp + m) * 6;
-                cp_async16(tdst + (slot * Nfp + m) * 6 + 2 * ch, src + 2 * ch);
-            }
-            cp_async_commit();
-        };
-        mbar_wait(&bars[WB_DG], 0);
-        issue_traces(0);
         for (int it = 0; it < nmine; it++) {
             const int par = it & 1, ph = (it >> 1) & 1, slot = it % 3;
-            if (it + 1 < nmine) {
-                mbar_wait(&bars[WB_DG + (it + 1) % 3], ((it + 1) / 3) & 1);
-                issue_traces(it + 1);
-                cp_async_wait_1();
-            } else cp_async_wait_all();
-            named_bar(1, B::NF);                               // every flux thread's trace copies are visible
+            mbar_wait(&bars[WB_TR + par], ph);                 // the traces of this batch have landed (issued by the LIFT warps)
             mbar_wait(&bars[WB_DG + slot], (it / 3) & 1);
             mbar_wait(&bars[WB_RAW + par], ph);
             if (it >= 2) mbar_wait(&bars[WB_FREE + par], ((it - 2) >> 1) & 1);
@@ -221,8 +226,7 @@ __global__ void __launch_bounds__(Ws<P>::T, 1) stage_ws_kernel(const MmaArgs A)
             const int code = info.y;
             const uint8_t *srow = sTab + f * Nfp;
             const double *ubase = raw + (g * Np * BLK_E + e8) * 6;
-            const uint8_t *nrow; const double *nbase; int nstride;
-            bool direct = false;
+            const uint8_t *nrow; const double *nbase = ubase; const double *gbase = nullptr; int nstride;
             double ce = 0.0, ch = 0.0, al = A.alpha;
             if (info.x >= 0) {
                 nrow = sTab + ((code >> FI_TAB_SHIFT) & FI_TAB_MASK) * Nfp;
@@ -232,15 +236,14 @@ __global__ void __launch_bounds__(Ws<P>::T, 1) stage_ws_kernel(const MmaArgs A)
                 ce = bc == 1 ? -2.0 : bc == 3 ? -1.0 : 0.0;
                 ch = bc == 2 ? -2.0 : bc == 3 ? -1.0 : 0.0;
                 if (bc == 3) al = 1.0;
-                nrow = srow; nbase = ubase; nstride = BLK_E * 6;
+                nrow = srow; nstride = BLK_E * 6;
             } else {
                 const int s = -2 - info.x;
                 if (s < CAP) { nrow = sIdent; nbase = tr + s * Nfp * 6; nstride = 6; }
                 else {   // more faces leave this batch than the trace buffer stages: read the trace from L2
                     const int2 d = reinterpret_cast<const int2 *>(dsc + EB * 8)[s];
-                    direct = true;
-                    if (d.x >= 0) { nrow = sTab + d.y * Nfp; nbase = A.yin + ((size_t)(d.x >> 3) * Np * BLK_E + (d.x & 7)) * 6; nstride = BLK_E * 6; }
-                    else { nrow = sIdent; nbase = A.halo + (size_t)(-1 - d.x) * Nfp * 6; nstride = 6; }
+                    if (d.x >= 0) { nrow = sTab + d.y * Nfp; gbase = A.yin + ((size_t)(d.x >> 3) * Np * BLK_E + (d.x & 7)) * 6; nstride = BLK_E * 6; }
+                    else { nrow = sIdent; gbase = A.halo + (size_t)(-1 - d.x) * Nfp * 6; nstride = 6; }
                 }
             }
             const int tf = (code >> FI_TFSF_SHIFT) & FI_TFSF_MASK;
@@ -255,18 +258,18 @@ __global__ void __launch_bounds__(Ws<P>::T, 1) stage_ws_kernel(const MmaArgs A)
             const double af = al * fs;
 #pragma unroll
             for (int mm = 0; mm < HN; mm++) {
-                const int m = h * HN + mm;
+                const int m = h + B::NH * mm;
                 if (m >= Nfp) break;
                 double uM[6], dU[6];
                 {
                     const double2 *pu = reinterpret_cast<const double2 *>(ubase + srow[m] * (BLK_E * 6));
                     const double2 v0 = pu[0], v1 = pu[1], v2 = pu[2];
                     double2 w0, w1, w2;
-                    if (!direct) {
+                    if (gbase == nullptr) {
                         const double2 *pn = reinterpret_cast<const double2 *>(nbase + nrow[m] * nstride);
                         w0 = pn[0]; w1 = pn[1]; w2 = pn[2];
                     } else {
-                        const double2 *pn = reinterpret_cast<const double2 *>(nbase + (size_t)nrow[m] * nstride);
+                        const double2 *pn = reinterpret_cast<const double2 *>(gbase + (size_t)nrow[m] * nstride);
                         w0 = __ldg(pn); w1 = __ldg(pn + 1); w2 = __ldg(pn + 2);
                     }
                     uM[0] = v0.x; uM[1] = v0.y; uM[2] = v1.x; uM[3] = v1.y; uM[4] = v2.x; uM[5] = v2.y;
