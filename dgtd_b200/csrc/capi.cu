@@ -9,6 +9,7 @@
 #include "kernels.cuh"
 #include "kernels_mma.cuh"
 #include "kernels_ws.cuh"
+#include "kernels_wg.cuh"
 
 #include <dlfcn.h>
 #include <cmath>
@@ -143,9 +144,33 @@ static bool select_ws(int dim, int p, MmaSet &ms)
     return false;
 }
 
+// the warp-per-group kernel: tetrahedra of order 1..4, element-major "aos" layout, one warp per group of 8 elements
+typedef void (*WgFn)(const WgArgs);
+struct WgSet { WgFn fn[4]; int threads; size_t smem; };
+template <int P> static WgSet wgset()
+{
+    using B = Wg<P>;
+    return {{stage_wg_kernel<P, 0>, stage_wg_kernel<P, 1>, stage_wg_kernel<P, 2>, stage_wg_kernel<P, 3>}, B::T, B::smem_bytes};
+}
+static bool select_wg(int dim, int p, WgSet &ws)
+{
+    if (dim != 3) return false;
+    switch (p) {
+        case 1: ws = wgset<1>(); return true; case 2: ws = wgset<2>(); return true;
+        case 3: ws = wgset<3>(); return true; case 4: ws = wgset<4>(); return true;
+    }
+    return false;
+}
+
 struct dgtd_ctx {
     HostOp H;
     BlockedPlan BP;
+    WgPlan WP;
+    bool has_sigma = false;
+    bool wg = false;                 // aos layout + warp-per-group kernel (blocked is set too: state needs layout conversion)
+    WgSet wgs{};
+    DevBuf<uint8_t> wtab;
+    DevBuf<int> dev2ref;
     bool blocked = false;            // state lives in the blocked layout and the DMMA stage kernel runs
     bool ws = false;                 // ... its warp-specialised variant
     bool identity = true;            // local element order == global order (single rank, no reordering)
@@ -227,7 +252,14 @@ static void launch_gate(dgtd_ctx *c, const double *ts, int nt)
 static void launch_stage(dgtd_ctx *c, int mode, StageArgs &A)
 {
     exchange(c, A.yin);
-    if (c->blocked) {
+    if (c->wg) {
+        WgArgs W;
+        W.bfrag = c->bafrag.p; W.geo = c->bgeo.p; W.desc = c->bdesc.p; W.tab = c->wtab.p; W.ntab = c->WP.ntab;
+        W.tfsf_xyz = A.tfsf_xyz; W.gate = A.gate; W.halo = A.halo; W.ngroups = c->WP.ngroups; W.has_sigma = c->has_sigma ? 1 : 0;
+        W.alpha = A.alpha; W.pw = A.pw; W.pw_on = A.pw_on;
+        W.yin = A.yin; W.x = A.x; W.z = A.z; W.yout = A.yout; W.a = A.a; W.b = A.b; W.t = A.t;
+        c->wgs.fn[mode]<<<c->grid, c->wgs.threads, c->wgs.smem, c->stream>>>(W);
+    } else if (c->blocked) {
         MmaArgs M;
         M.afrag = c->bafrag.p; M.geo = c->bgeo.p; M.desc = c->bdesc.p; M.ftab = c->ftab.p; M.ntab = c->H.ntab;
         M.tfsf_xyz = A.tfsf_xyz; M.gate = A.gate; M.halo = A.halo; M.nbatch = c->BP.nbatch; M.alpha = A.alpha; M.pw = A.pw; M.pw_on = A.pw_on;
@@ -269,6 +301,20 @@ static void mult_device(dgtd_ctx *c, double t, const double *in, double *out)
     launch_stage(c, MODE_MULT, A);
 }
 
+// reference-layout device vector [6][Nloc] <-> the kernel's state layout (blocked, or aos for the warp-per-group kernel)
+static void to_device_layout(dgtd_ctx *c, const double *ref, double *dev)
+{
+    if (c->wg) to_aos_kernel<<<1184, 256, 0, c->stream>>>(ref, c->Nloc, c->H.Np, c->H.NEloc, c->WP.NEpad, c->dev2ref.p, dev);
+    else to_blocked_kernel<<<1184, 256, 0, c->stream>>>(ref, c->Nloc, c->H.Np, c->H.NEloc, c->BP.NEpad, dev);
+    c->launches++;
+}
+static void from_device_layout(dgtd_ctx *c, const double *dev, double *ref)
+{
+    if (c->wg) from_aos_kernel<<<1184, 256, 0, c->stream>>>(dev, c->Nloc, c->H.Np, c->H.NEloc, c->dev2ref.p, ref);
+    else from_blocked_kernel<<<1184, 256, 0, c->stream>>>(dev, c->Nloc, c->H.Np, c->H.NEloc, ref);
+    c->launches++;
+}
+
 // local reference-layout host vector [6][Nloc] <-> device state (reference layout, or blocked through a staging buffer)
 static void upload_local(dgtd_ctx *c, const double *hloc, double *dev)
 {
@@ -278,8 +324,7 @@ static void upload_local(dgtd_ctx *c, const double *hloc, double *dev)
     } else {
         if (c->stage_ref.n != (size_t)6 * Nl) c->stage_ref.alloc((size_t)6 * Nl);
         CU(cudaMemcpyAsync(c->stage_ref.p, hloc, sizeof(double) * 6 * Nl, cudaMemcpyHostToDevice, c->stream));
-        to_blocked_kernel<<<1184, 256, 0, c->stream>>>(c->stage_ref.p, Nl, c->H.Np, c->H.NEloc, c->BP.NEpad, dev);
-        c->launches++;
+        to_device_layout(c, c->stage_ref.p, dev);
     }
     CU(cudaStreamSynchronize(c->stream));
 }
@@ -290,8 +335,7 @@ static void download_local(dgtd_ctx *c, const double *dev, double *hloc)
         CU(cudaMemcpyAsync(hloc, dev, sizeof(double) * 6 * Nl, cudaMemcpyDeviceToHost, c->stream));
     } else {
         if (c->stage_ref.n != (size_t)6 * Nl) c->stage_ref.alloc((size_t)6 * Nl);
-        from_blocked_kernel<<<1184, 256, 0, c->stream>>>(dev, Nl, c->H.Np, c->H.NEloc, c->stage_ref.p);
-        c->launches++;
+        from_device_layout(c, dev, c->stage_ref.p);
         CU(cudaMemcpyAsync(hloc, c->stage_ref.p, sizeof(double) * 6 * Nl, cudaMemcpyDeviceToHost, c->stream));
     }
     CU(cudaStreamSynchronize(c->stream));
@@ -437,12 +481,25 @@ int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
     int G = groups ? std::atoi(groups) : 1;
     bool has_sigma = false;
     for (int le = 0; le < H.NEloc; le++) has_sigma |= H.geo[(size_t)le * GEO_STRIDE + 15] != 0.0;
+    c->has_sigma = has_sigma;
     const bool tabs_ok = H.ntab <= 128;
-    if (ksel != "generic" && tabs_ok) {
+    if (ksel == "wg" && select_wg(H.dim, H.p, c->wgs) && c->wgs.smem <= (size_t)prop.sharedMemPerBlockOptin) {
+        c->WP = build_wg_plan(H);
+        if (c->WP.ntab <= Wg<3>::TABROWS) c->blocked = c->wg = true;
+    }
+    if (c->wg) {
+        c->Nalloc = (long long)c->WP.NEpad * H.Np;
+        for (int m = 0; m < 4; m++) CU(cudaFuncSetAttribute((const void *)c->wgs.fn[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->wgs.smem));
+        const int nw = c->wgs.threads / 32;
+        c->grid = (int)std::min<long long>(((long long)c->WP.ngroups + nw - 1) / nw, (long long)prop.multiProcessorCount);
+        c->bgeo.upload(c->WP.geo); c->bafrag.upload(c->WP.bfrag); c->bdesc.upload(c->WP.desc); c->bsend_off.upload(c->WP.send_off, 1);
+        c->wtab.upload(c->WP.tab, 16); c->dev2ref.upload(c->WP.dev2ref);
+    } else if (ksel != "generic" && tabs_ok) {
         if (ksel != "mma" && !has_sigma && select_ws(H.dim, H.p, c->ms) && c->ms.smem <= (size_t)prop.sharedMemPerBlockOptin) { c->blocked = c->ws = true; G = 2; }
         else if (select_mma(H.dim, H.p, G, c->ms) || select_mma(H.dim, H.p, G = 1, c->ms)) c->blocked = c->ms.smem <= (size_t)prop.sharedMemPerBlockOptin;
     }
-    if (c->blocked) {
+    if (c->wg) {
+    } else if (c->blocked) {
         c->BP = build_blocked_plan(H, G);
         c->Nalloc = (long long)c->BP.NEpad * H.Np;
         for (int m = 0; m < 4; m++) CU(cudaFuncSetAttribute((const void *)c->ms.fn[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ms.smem));
@@ -572,10 +629,9 @@ int dgtd_mult(dgtd_ctx *c, double t, const double *in, double *out, int on_devic
     else {
         if (c->tmp_in.n != n6) { c->tmp_in.alloc(n6); c->tmp_out.alloc(n6); }
         if (on_device) {   // reference-layout device vectors [6][n_local] <-> blocked
-            to_blocked_kernel<<<1184, 256, 0, c->stream>>>(in, c->Nloc, c->H.Np, c->H.NEloc, c->BP.NEpad, c->tmp_in.p);
+            to_device_layout(c, in, c->tmp_in.p);
             mult_device(c, t, c->tmp_in.p, c->tmp_out.p);
-            from_blocked_kernel<<<1184, 256, 0, c->stream>>>(c->tmp_out.p, c->Nloc, c->H.Np, c->H.NEloc, out);
-            c->launches += 2;
+            from_device_layout(c, c->tmp_out.p, out);
         } else {
             scatter_to_device(c, in, c->tmp_in.p);
             mult_device(c, t, c->tmp_in.p, c->tmp_out.p);
@@ -624,7 +680,8 @@ int dgtd_sample(dgtd_ctx *c, int npts, const int *elem, const double *shape, dou
     de.alloc(npts); ds.alloc((size_t)npts * c->H.Np); dout.alloc((size_t)npts * 6);
     CU(cudaMemcpyAsync(de.p, elem, sizeof(int) * npts, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(ds.p, shape, sizeof(double) * npts * c->H.Np, cudaMemcpyHostToDevice, c->stream));
-    if (c->blocked) sample_blocked_kernel<<<(npts + 127) / 128, 128, 0, c->stream>>>(c->x.p, c->H.Np, npts, de.p, ds.p, dout.p);
+    if (c->wg) sample_aos_kernel<<<(npts + 127) / 128, 128, 0, c->stream>>>(c->x.p, c->H.Np, npts, de.p, ds.p, c->dev2ref.p, dout.p);
+    else if (c->blocked) sample_blocked_kernel<<<(npts + 127) / 128, 128, 0, c->stream>>>(c->x.p, c->H.Np, npts, de.p, ds.p, dout.p);
     else sample_kernel<<<(npts + 127) / 128, 128, 0, c->stream>>>(c->x.p, c->Nloc, c->H.Np, npts, de.p, ds.p, dout.p);
     c->launches++;
     CU(cudaMemcpyAsync(out6, dout.p, sizeof(double) * npts * 6, cudaMemcpyDeviceToHost, c->stream));
@@ -644,7 +701,10 @@ int dgtd_kernel_info(const dgtd_ctx *c, char *buf, int cap)
 {
     if (!c || !buf || cap < 1) return fail(DGTD_ERR_ARG, "bad argument");
     char tmp[256];
-    if (c->blocked)
+    if (c->wg)
+        std::snprintf(tmp, sizeof tmp, "stage_wg_kernel<P=%d,MODE> DMMA m8n8k4 transposed, warp per group of 8 elements, aos layout, %d threads, %zu B smem, grid %d",
+                      c->H.p, c->wgs.threads, c->wgs.smem, c->grid);
+    else if (c->blocked)
         std::snprintf(tmp, sizeof tmp, "%s<P=%d,G=%d,MODE> DMMA m8n8k4, blocked layout, %d threads, %zu B smem, grid %d",
                       c->ws ? "stage_ws_kernel" : "stage_mma_kernel", c->H.p, c->BP.G, c->ms.threads, c->ms.smem, c->grid);
     else

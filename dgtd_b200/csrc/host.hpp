@@ -124,6 +124,25 @@ struct BlockedPlan {
 };
 BlockedPlan build_blocked_plan(const HostOp &H, int G);
 inline long long blocked_offset(int Np, long long le, int node) { return (((le >> 3) * Np + node) * BLK_E + (le & 7)) * 6; }
+// ---- "wg" plan of the warp-per-group DMMA stage kernel (3-D only) --------------------------------------------------------
+// Device state layout "aos": element-major node records, offset(e, n, c) = ((e * Np) + n) * 6 + c with n the DEVICE node
+// id (dev2ref maps it to the reference node); 8 consecutive local elements form a group = one warp's unit of work, one
+// contiguous chunk of Np*8*6 doubles.  The contraction runs "transposed" (DMMA A = data [8 elements x 4 nodes],
+// B = operator [4 nodes x 8 output nodes]) so that a lane owns one element through all phases.
+struct WgPlan {
+    int ngroups = 0, NEpad = 0;
+    int NT = 0, KSV = 0;               // output n-tiles (the last one is "mixed"), k-steps of the volume contraction
+    int nfrag_vol = 0, nfrag_lift = 0; // B fragments of 32 doubles: volume [KSV][(NT-1)*3 + 3], LIFT [Nfp][NT]
+    std::vector<int> dev2ref, ref2dev; // Np
+    std::vector<int> forder;           // 4*Nfp : step s of face f handles canonical face node forder[f*Nfp+s]
+    std::vector<double> geo;           // NEpad * BLK_GEO
+    std::vector<int> desc;             // NEpad*4*2 : {nbr local element | -1 boundary | -2-haloFace, code (FI_TAB = row of tab)}
+    std::vector<uint8_t> tab;          // ntab*16 : rows 0..3 own device node per step, 4..7 canonical index per step, 8.. neighbour device node per step
+    int ntab = 0;
+    std::vector<double> bfrag;         // (nfrag_vol + nfrag_lift) * 32
+    std::vector<long long> send_off;   // nSendFaces*Nfp : offset (doubles) of the node record in the aos state
+};
+WgPlan build_wg_plan(const HostOp &H);
 void node_coords(const Mesh &m, const RefElem &ref, std::vector<double> &xyz);   // [NE*Np][3], global numbering
 
 }  // namespace dgtd

@@ -1,0 +1,371 @@
+// sm_100a warp-per-group DMMA stage kernel (tetrahedra): one warp carries a group of 8 elements through the whole fused
+// stage — covariant transform, volume contraction, face flux, LIFT, push-forward, Runge-Kutta update — in registers.
+//
+// Why (profiles/r1_ws_stage_ncu_summary.txt): the role-specialised kernel moves every intermediate (covariant field,
+// flux, partial results) through shared memory between warps, which puts the LSU pipe at 54 % next to an FP64 pipe at
+// 61 % and leaves both waiting on hand-over barriers.  Here the contraction is TRANSPOSED: the DMMA A operand is the data
+// [8 elements x 4 nodes] and the B operand the operator [4 nodes x 8 output nodes], so lane (e = l>>2, j = l&3) owns
+// element e as A-row, as accumulator row and in the element-wise phases:
+//   volume   lane reads the node record (e, 4ks + j) of y_in, forms u~ = J^T u / det J in registers, feeds it as A;
+//   flux     lane = (element e, face j): per step s it forms the contravariant flux at face node s of its face and feeds
+//            it as A of the LIFT contraction (K = 4 faces x Nfp nodes, k-lane j = face j: geometry set up once per lane);
+//   epilogue lane holds k~ of (e, nodes 8nt + j, 8nt + j + 4) for all six components: push-forward with J, material,
+//            RK update on the x / z records, in place in shared memory.
+// Warps never synchronise with each other: a warp has its own three group buffers (y_in, x -> y_out, z -> z_new), filled
+// and drained by bulk-TMA copies on per-warp mbarriers, and its own geometry/descriptor slice.  The operator B fragments
+// (19 KB at order 3) sit in shared memory once per CTA.  Neighbour traces of faces leaving the group are read straight from
+// y_in in global memory (L2) through the generic address path, prefetched one step ahead.
+// State layout "aos" (host.hpp, WgPlan): offset(e, n, c) = (e * Np + n) * 6 + c.
+// Reference semantics: src/evolution/HesthavenEvolution.cpp:450-542 with the `global` operator's coefficients
+// (src/components/DGOperatorFactory.h:469-573, 1268-1361), external/mfem-geg/linalg/ode.cpp:109-136.
+#pragma once
+#include "kernels_mma.cuh"
+
+namespace dgtd {
+
+struct WgArgs {
+    const double *bfrag;      // WgPlan::bfrag
+    const double *geo;        // [NEpad][32]
+    const int *desc;          // [NEpad][4] int2
+    const uint8_t *tab;       // [ntab][16]
+    int ntab;
+    const double *tfsf_xyz;
+    const double *gate;
+    const double *halo;       // [haloFace][Nfp][6]
+    int ngroups;
+    int has_sigma;
+    double alpha;
+    DevPlaneWave pw;
+    int pw_on;
+    const double *yin, *x;    // aos layout
+    double *z, *yout;
+    double a, b, t;
+};
+
+template <int P> struct Wg {
+    static constexpr int Np = (P + 1) * (P + 2) * (P + 3) / 6, Nfp = (P + 1) * (P + 2) / 2;
+    static constexpr int NT = (Np + 7) / 8, KSV = (Np + 3) / 4, VT = (NT - 1) * 3 + 3;
+    static constexpr int NW = P <= 3 ? 8 : 4, T = 32 * NW;       // warps per CTA = groups in flight per SM
+    static constexpr int GS = Np * BLK_E * 6;                    // doubles per group of one state vector
+    static constexpr int NFV = KSV * VT, NFL = Nfp * NT, NFR = NFV + NFL;
+    static constexpr int WGEO = BLK_E * BLK_GEO, WDESC = BLK_E * 4 * 2;   // doubles / ints per group
+    static constexpr int WDBL = 3 * GS + WGEO + WDESC / 2;       // doubles per warp: Y, X, Z, geometry, descriptors
+    static constexpr int TABROWS = 136;
+    static constexpr int oWarp = NFR * 32;
+    static constexpr size_t bTab = (size_t)(oWarp + NW * WDBL) * 8;
+    static constexpr size_t bBar = bTab + (size_t)TABROWS * 16;
+    static constexpr size_t smem_bytes = bBar + (size_t)NW * 2 * 8;
+    static_assert(Np - 8 * (NT - 1) <= 4, "mixed last tile");
+    static_assert((GS % 2) == 0 && (bTab % 16) == 0, "alignment");
+};
+
+__device__ __forceinline__ int tab_byte(const uint4 &r, int s)
+{
+    const uint32_t w = (s >> 2) == 0 ? r.x : (s >> 2) == 1 ? r.y : (s >> 2) == 2 ? r.z : r.w;
+    return (int)((w >> (8 * (s & 3))) & 0xffu);
+}
+// 48-byte node record through the generic address path (shared or global)
+__device__ __forceinline__ void load_rec(const double *p, double *u)
+{
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    const double2 a = q[0], b = q[1], c = q[2];
+    u[0] = a.x; u[1] = a.y; u[2] = b.x; u[3] = b.y; u[4] = c.x; u[5] = c.y;
+}
+__device__ __forceinline__ void store_rec(double *p, const double *u)
+{
+    double2 *q = reinterpret_cast<double2 *>(p);
+    q[0] = make_double2(u[0], u[1]); q[1] = make_double2(u[2], u[3]); q[2] = make_double2(u[4], u[5]);
+}
+
+template <int P, int MODE>
+__global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
+{
+    using B = Wg<P>;
+    constexpr int Np = B::Np, Nfp = B::Nfp, NT = B::NT, KSV = B::KSV, VT = B::VT, GS = B::GS;
+    constexpr int NL = Np - 8 * (NT - 1);                                          // nodes of the mixed tile
+    constexpr bool LOAD_X = MODE == MODE_STAGE1 || MODE == MODE_STAGE23;           // stage 1: x == y_in, fetched again (L2 hit)
+    constexpr bool LOAD_Z = MODE == MODE_STAGE23 || MODE == MODE_STAGE4;
+    constexpr bool STORE_X = MODE != MODE_STAGE4, STORE_Z = MODE != MODE_MULT;      // stage 4 forms the new x in the z buffer
+    extern __shared__ __align__(128) unsigned char smem_wg[];
+    double *sm = reinterpret_cast<double *>(smem_wg);
+    const double *sFragV = sm, *sFragL = sm + B::NFV * 32;
+    const uint4 *sTab = reinterpret_cast<const uint4 *>(smem_wg + B::bTab);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, e = lane >> 2, j = lane & 3;
+    double *wY = sm + B::oWarp + warp * B::WDBL, *wX = wY + GS, *wZ = wX + GS, *wGeo = wZ + GS;
+    const int2 *wDesc = reinterpret_cast<const int2 *>(wGeo + B::WGEO);
+    uint64_t *barY = reinterpret_cast<uint64_t *>(smem_wg + B::bBar) + 2 * warp, *barXZ = barY + 1;
+
+    for (int i = tid; i < B::NFR * 32; i += B::T) sm[i] = A.bfrag[i];
+    {
+        uint4 *dst = reinterpret_cast<uint4 *>(smem_wg + B::bTab);
+        const uint4 *src = reinterpret_cast<const uint4 *>(A.tab);
+        for (int i = tid; i < min(A.ntab, B::TABROWS); i += B::T) dst[i] = src[i];
+    }
+    if (lane == 0) { mbar_init(barY, 1); mbar_init(barXZ, 1); }
+    if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem();
+    __syncthreads();
+
+    const int gstride = gridDim.x * B::NW;
+    int g = blockIdx.x * B::NW + warp;
+    if (g >= A.ngroups) return;
+    const uint4 ownrow = sTab[j];
+    const bool inject = A.pw_on && (A.gate == nullptr || *A.gate >= 1e-16);
+
+    auto issue_y = [&](int gg) {
+        mbar_expect_tx(barY, (uint32_t)(GS * 8 + B::WGEO * 8 + B::WDESC * 4));
+        bulk_load(wY, A.yin + (size_t)gg * GS, GS * 8, barY);
+        bulk_load(wGeo, A.geo + (size_t)gg * B::WGEO, B::WGEO * 8, barY);
+        bulk_load(wGeo + B::WGEO, A.desc + (size_t)gg * B::WDESC, B::WDESC * 4, barY);
+    };
+    auto issue_xz = [&](int gg) {
+        mbar_expect_tx(barXZ, (uint32_t)(GS * 8) * ((LOAD_X ? 1 : 0) + (LOAD_Z ? 1 : 0)));
+        if (LOAD_X) bulk_load(wX, (MODE == MODE_STAGE1 ? A.yin : A.x) + (size_t)gg * GS, GS * 8, barXZ);
+        if (LOAD_Z) bulk_load(wZ, A.z + (size_t)gg * GS, GS * 8, barXZ);
+    };
+    if (lane == 0) { issue_y(g); if (LOAD_X || LOAD_Z) issue_xz(g); }
+
+    for (int it = 0; g < A.ngroups; g += gstride, it++) {
+        const uint32_t par = it & 1;
+        const double *ge = wGeo + e * BLK_GEO;
+        const double *yrec = wY + e * Np * 6;
+        mbar_wait(barY, par);
+
+        double acc[6][NT][2];
+#pragma unroll
+        for (int c = 0; c < 6; c++)
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++) acc[c][nt][0] = acc[c][nt][1] = 0.0;
+        // The mixed tile (nt = NT-1) of field fo keeps, for input component x, the accumulator acc[3 fo + x][NT-1]:
+        // element 0 -> k~_{x+1}, element 1 -> k~_{x+2} (volume); the LIFT of component c adds to acc[3 fo + (c+2)%3][NT-1][0].
+
+        // ---------------- volume: k~E_c = D_{c+1} u~H_{c+2} - D_{c+2} u~H_{c+1},  k~H likewise from u~E = -J^T E / det ------
+        {
+            double jm[9];
+#pragma unroll
+            for (int i = 0; i < 9; i++) jm[i] = ge[i];
+            const double idet = ge[22], nidet = -idet;
+#pragma unroll
+            for (int ks = 0; ks < KSV; ks++) {
+                const int node = 4 * ks + j;
+                double u[6] = {0, 0, 0, 0, 0, 0};
+                if (4 * ks + 3 < Np || node < Np) load_rec(yrec + node * 6, u);
+                double ut[6];     // [0..2] u~E, [3..5] u~H
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    ut[a] = fma(jm[a], u[0], fma(jm[3 + a], u[1], jm[6 + a] * u[2])) * nidet;
+                    ut[3 + a] = fma(jm[a], u[3], fma(jm[3 + a], u[4], jm[6 + a] * u[5])) * idet;
+                }
+                const double *fr = sFragV + (ks * VT) * 32 + lane;
+#pragma unroll
+                for (int nt = 0; nt < NT - 1; nt++)
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        const double bv = fr[(nt * 3 + d) * 32];
+                        const int cp = (d + 2) % 3, cm = (d + 1) % 3;      // acc[cp] += D_d u~[d+1] ; acc[cm] -= D_d u~[d+2]
+                        dmma884(acc[cp][nt][0], acc[cp][nt][1], ut[3 + (d + 1) % 3], bv);
+                        dmma884(acc[cm][nt][0], acc[cm][nt][1], -ut[3 + (d + 2) % 3], bv);
+                        dmma884(acc[3 + cp][nt][0], acc[3 + cp][nt][1], ut[(d + 1) % 3], bv);
+                        dmma884(acc[3 + cm][nt][0], acc[3 + cm][nt][1], -ut[(d + 2) % 3], bv);
+                    }
+#pragma unroll
+                for (int x = 0; x < 3; x++) {
+                    const double bv = fr[((NT - 1) * 3 + x) * 32];
+                    dmma884(acc[x][NT - 1][0], acc[x][NT - 1][1], ut[3 + x], bv);
+                    dmma884(acc[3 + x][NT - 1][0], acc[3 + x][NT - 1][1], ut[x], bv);
+                }
+            }
+        }
+        // x / z of this group: the previous group's stores have long drained the buffers
+        if ((LOAD_X || LOAD_Z) && it > 0 && lane == 0) { bulk_wait_read(); issue_xz(g); }
+
+        // ---------------- face flux of (element e, face j) -> LIFT --------------------------------------------------------
+        {
+            const int2 info = wDesc[e * 4 + j];
+            const int code = info.y;
+            const double *nbase = yrec;
+            uint4 nrow = ownrow;
+            double ce = 0.0, ch = 0.0, al = A.alpha;
+            if (info.x >= 0) {
+                nrow = sTab[(code >> FI_TAB_SHIFT) & FI_TAB_MASK];
+                nbase = (info.x >> 3) == g ? wY + (info.x & 7) * Np * 6 : A.yin + (size_t)info.x * Np * 6;
+            } else if (info.x == -1) {
+                const int bc = code & FI_BC_MASK;
+                ce = bc == 1 ? -2.0 : bc == 3 ? -1.0 : 0.0;
+                ch = bc == 2 ? -2.0 : bc == 3 ? -1.0 : 0.0;
+                if (bc == 3) al = 1.0;
+            } else {
+                nrow = sTab[4 + j];
+                nbase = A.halo + (size_t)(-2 - info.x) * Nfp * 6;
+            }
+            const int tf = (code >> FI_TFSF_SHIFT) & FI_TFSF_MASK;
+            double ji[9];
+#pragma unroll
+            for (int i = 0; i < 9; i++) ji[i] = ge[9 + i];
+            double gn[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) gn[d] = j == 0 ? (ji[d] + ji[3 + d]) + ji[6 + d] : -ji[3 * (j - 1) + d];   // -grad lambda_j: outward
+            const double fs = ge[18 + j];
+            const double ifs = 1.0 / fs, ifs2 = ifs * ifs;
+            const double af = al * fs;
+            double uP[6];
+            load_rec(nbase + tab_byte(nrow, 0) * 6, uP);
+#pragma unroll
+            for (int s = 0; s < Nfp; s++) {
+                double uM[6], uN[6], dU[6];
+                load_rec(yrec + tab_byte(ownrow, s) * 6, uM);
+                if (s + 1 < Nfp) load_rec(nbase + tab_byte(nrow, s + 1) * 6, uN);
+#pragma unroll
+                for (int c = 0; c < 3; c++) { dU[c] = fma(ce, uM[c], uP[c] - uM[c]); dU[3 + c] = fma(ch, uM[3 + c], uP[3 + c] - uM[3 + c]); }
+                if (tf && inject) {
+                    double inc[6];
+                    const int m = tab_byte(sTab[4 + j], s);
+                    planewave6(A.pw, A.tfsf_xyz + ((long long)(code >> FI_TIDX_SHIFT) * Nfp + m) * 3, A.t, inc);
+                    const double sg = tf == 1 ? 1.0 : -1.0;
+#pragma unroll
+                    for (int c = 0; c < 6; c++) dU[c] += sg * inc[c];
+                }
+                const double gdE = (gn[0] * dU[0] + gn[1] * dU[1] + gn[2] * dU[2]) * ifs2;
+                const double gdH = (gn[0] * dU[3] + gn[1] * dU[4] + gn[2] * dU[5]) * ifs2;
+                double fl[6];
+                fl[0] = (gn[1] * dU[5] - gn[2] * dU[4]) + af * (dU[0] - gdE * gn[0]);
+                fl[1] = (gn[2] * dU[3] - gn[0] * dU[5]) + af * (dU[1] - gdE * gn[1]);
+                fl[2] = (gn[0] * dU[4] - gn[1] * dU[3]) + af * (dU[2] - gdE * gn[2]);
+                fl[3] = -(gn[1] * dU[2] - gn[2] * dU[1]) + af * (dU[3] - gdH * gn[0]);
+                fl[4] = -(gn[2] * dU[0] - gn[0] * dU[2]) + af * (dU[4] - gdH * gn[1]);
+                fl[5] = -(gn[0] * dU[1] - gn[1] * dU[0]) + af * (dU[5] - gdH * gn[2]);
+                double ft[6];
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    ft[a] = fma(ji[3 * a], fl[0], fma(ji[3 * a + 1], fl[1], ji[3 * a + 2] * fl[2]));
+                    ft[3 + a] = fma(ji[3 * a], fl[3], fma(ji[3 * a + 1], fl[4], ji[3 * a + 2] * fl[5]));
+                }
+                const double *fr = sFragL + (s * NT) * 32 + lane;
+#pragma unroll
+                for (int nt = 0; nt < NT - 1; nt++) {
+                    const double bv = fr[nt * 32];
+#pragma unroll
+                    for (int c = 0; c < 6; c++) dmma884(acc[c][nt][0], acc[c][nt][1], ft[c], bv);
+                }
+                {
+                    const double bv = fr[(NT - 1) * 32];
+#pragma unroll
+                    for (int c = 0; c < 6; c++) {
+                        const int xa = 3 * (c / 3) + (c % 3 + 2) % 3;
+                        dmma884(acc[xa][NT - 1][0], acc[xa][NT - 1][1], ft[c], bv);
+                    }
+                }
+                if (s + 1 < Nfp) {
+#pragma unroll
+                    for (int c = 0; c < 6; c++) uP[c] = uN[c];
+                }
+            }
+        }
+
+        // ---------------- push forward, material, Runge-Kutta stage ---------------------------------------------------------
+        double jm[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) jm[i] = ge[i];
+        const double ie = ge[23], im = ge[24], se = ge[25];
+        const bool keep_y = A.has_sigma != 0;        // the conductivity term reads E of y_in in the epilogue
+        const int gnext = g + gstride;
+        if (!keep_y) {
+            __syncwarp();
+            if (lane == 0 && gnext < A.ngroups) issue_y(gnext);
+        }
+        if (LOAD_X || LOAD_Z) mbar_wait(barXZ, par);
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int node = nt < NT - 1 ? 8 * nt + j + 4 * h : 8 * (NT - 1) + j;
+                if (nt == NT - 1 && h == 1) continue;
+                if (nt == NT - 1 && NL < 4 && j >= NL) continue;
+                double kr[6];
+                if (nt < NT - 1) {
+#pragma unroll
+                    for (int c = 0; c < 6; c++) kr[c] = acc[c][nt][h];
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 6; c++) {
+                        const int f3 = 3 * (c / 3), cc = c % 3;
+                        kr[c] = acc[f3 + (cc + 2) % 3][NT - 1][0] + acc[f3 + (cc + 1) % 3][NT - 1][1];
+                    }
+                }
+                double k[6];
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    k[d] = fma(jm[3 * d], kr[0], fma(jm[3 * d + 1], kr[1], jm[3 * d + 2] * kr[2])) * ie;
+                    k[3 + d] = fma(jm[3 * d], kr[3], fma(jm[3 * d + 1], kr[4], jm[3 * d + 2] * kr[5])) * im;
+                }
+                const int off = (e * Np + node) * 6;
+                if (keep_y) {
+                    double uo[6];
+                    load_rec(wY + off, uo);
+#pragma unroll
+                    for (int d = 0; d < 3; d++) k[d] -= se * uo[d];
+                }
+                double xv[6], zv[6], o[6], zn[6];
+                if (LOAD_X) load_rec(wX + off, xv);
+                if (LOAD_Z) load_rec(wZ + off, zv);
+#pragma unroll
+                for (int c = 0; c < 6; c++) {
+                    if (MODE == MODE_MULT) o[c] = k[c];
+                    else if (MODE == MODE_STAGE1) { o[c] = fma(A.a, k[c], xv[c]); zn[c] = fma(A.b, k[c], xv[c]); }
+                    else if (MODE == MODE_STAGE23) { o[c] = fma(A.a, k[c], xv[c]); zn[c] = fma(A.b, k[c], zv[c]); }
+                    else zn[c] = fma(A.b, k[c], zv[c]);            // stage 4: new x, formed in the z buffer
+                }
+                if (STORE_X) store_rec(wX + off, o);
+                if (STORE_Z) store_rec(wZ + off, zn);
+            }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            const size_t goff = (size_t)g * GS;
+            if (STORE_X) bulk_store(A.yout + goff, wX, GS * 8);
+            if (MODE == MODE_STAGE4) bulk_store(A.yout + goff, wZ, GS * 8);
+            else if (STORE_Z) bulk_store(A.z + goff, wZ, GS * 8);
+            bulk_commit();
+            if (keep_y && gnext < A.ngroups) issue_y(gnext);
+            if (!(LOAD_X || LOAD_Z)) bulk_wait_read();            // the next epilogue writes these buffers again
+        }
+        __syncwarp();
+    }
+    if (lane == 0) bulk_wait_all();
+}
+
+// ---- layout conversion between the reference layout [6][Nloc] (Fields.h:45-65) and the aos device layout ---------------
+__global__ void to_aos_kernel(const double *ref, long long stride, int Np, long long NEloc, long long NEpad, const int *dev2ref, double *aos)
+{
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < NEpad * Np; idx += (long long)gridDim.x * blockDim.x) {
+        const long long e = idx / Np; const int n = (int)(idx - e * Np);
+        double *o = aos + idx * 6;
+        const long long src = e * Np + dev2ref[n];
+#pragma unroll
+        for (int c = 0; c < 6; c++) o[c] = e < NEloc ? ref[c * stride + src] : 0.0;
+    }
+}
+__global__ void from_aos_kernel(const double *aos, long long stride, int Np, long long NEloc, const int *dev2ref, double *ref)
+{
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < NEloc * Np; idx += (long long)gridDim.x * blockDim.x) {
+        const long long e = idx / Np; const int n = (int)(idx - e * Np);
+        const double *o = aos + idx * 6;
+        const long long dst = e * Np + dev2ref[n];
+#pragma unroll
+        for (int c = 0; c < 6; c++) ref[c * stride + dst] = o[c];
+    }
+}
+__global__ void sample_aos_kernel(const double *y, int Np, int npts, const int *elem, const double *shape, const int *dev2ref, double *out)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npts) return;
+    const long long e = elem[p];
+    for (int c = 0; c < 6; c++) {
+        double s = 0;
+        for (int n = 0; n < Np; n++) s = fma(shape[(long long)p * Np + dev2ref[n]], y[(e * Np + n) * 6 + c], s);
+        out[p * 6 + c] = s;
+    }
+}
+
+}  // namespace dgtd

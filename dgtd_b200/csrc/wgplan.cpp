@@ -1,0 +1,124 @@
+// Host-side plan of the warp-per-group DMMA stage kernel (kernels_wg.cuh): element-major state layout, per-face
+// descriptors, neighbour node tables and the operator B-fragments of the "transposed" contraction.
+// Pure data re-arrangement of HostOp (setup.cpp); the arithmetic it prepares is the reference's
+//   per-element D_x/D_y/D_z, normals, fscale, LIFT     src/evolution/HesthavenEvolution.cpp:150-205, 56-81
+//   vmapM/vmapP                                         src/evolution/HesthavenEvolutionMethods.cpp:501-534
+// with the volume term evaluated as a reference-space curl of the covariant field (see blocked.cpp).
+#include "host.hpp"
+#include "../../include/dgtd_b200.h"
+
+#include <algorithm>
+#include <map>
+
+namespace dgtd {
+
+WgPlan build_wg_plan(const HostOp &H)
+{
+    if (H.dim != 3) throw Error(DGTD_ERR_UNSUPPORTED, "the warp-per-group kernel covers tetrahedra only");
+    WgPlan W;
+    const int Np = H.Np, Nfp = H.Nfp, NE = H.NEloc;
+    if (Nfp > 16) throw Error(DGTD_ERR_UNSUPPORTED, "face node rows are 16 bytes");
+    W.ngroups = (NE + BLK_E - 1) / BLK_E;
+    W.NEpad = W.ngroups * BLK_E;
+    const int NT = W.NT = (Np + 7) / 8, KSV = W.KSV = (Np + 3) / 4;
+    if (Np - 8 * (NT - 1) > 4) throw Error(DGTD_ERR_UNSUPPORTED, "the mixed last tile holds at most 4 output nodes");
+
+    // ---- device node numbering and per-face step order (identity; hooks for bank-conflict-free orders) ----------------
+    W.dev2ref.resize(Np); W.ref2dev.resize(Np);
+    for (int n = 0; n < Np; n++) W.dev2ref[n] = W.ref2dev[n] = n;
+    W.forder.resize((size_t)4 * Nfp);
+    for (int f = 0; f < 4; f++) for (int s = 0; s < Nfp; s++) W.forder[(size_t)f * Nfp + s] = s;
+
+    // ---- geometry records (same record as the blocked plan) --------------------------------------------------------------
+    W.geo.assign((size_t)W.NEpad * BLK_GEO, 0.0);
+    for (int e = 0; e < W.NEpad; e++) {
+        double *g = &W.geo[(size_t)e * BLK_GEO];
+        if (e < NE) {
+            const double *v1 = &H.geo[(size_t)e * GEO_STRIDE], *jc = &H.jac[(size_t)e * 10];
+            for (int i = 0; i < 9; i++) { g[i] = jc[i]; g[9 + i] = v1[i]; }
+            for (int f = 0; f < 4; f++) g[18 + f] = v1[9 + f];
+            g[22] = 1.0 / jc[9]; g[23] = v1[13]; g[24] = v1[14]; g[25] = v1[15];
+        } else {   // padding element: unit geometry, vacuum; its state stays zero
+            g[0] = g[4] = g[8] = 1.0; g[9] = g[13] = g[17] = 1.0;
+            g[18] = g[19] = g[20] = g[21] = 1.0; g[22] = g[23] = g[24] = 1.0;
+        }
+    }
+
+    // ---- node tables: 16-byte rows indexed by the step s of a face ---------------------------------------------------------
+    auto put_row = [&](const std::vector<uint8_t> &row) { W.tab.insert(W.tab.end(), row.begin(), row.end()); return W.ntab++; };
+    for (int f = 0; f < 4; f++) {   // rows 0..3: own device node
+        std::vector<uint8_t> row(16, 0);
+        for (int s = 0; s < Nfp; s++) row[s] = (uint8_t)W.ref2dev[H.ref.fnodes[(size_t)f * Nfp + W.forder[(size_t)f * Nfp + s]]];
+        put_row(row);
+    }
+    for (int f = 0; f < 4; f++) {   // rows 4..7: canonical face-node index (halo buffer, TF/SF coordinates)
+        std::vector<uint8_t> row(16, 0);
+        for (int s = 0; s < Nfp; s++) row[s] = (uint8_t)W.forder[(size_t)f * Nfp + s];
+        put_row(row);
+    }
+    std::map<std::pair<int, int>, int> rowOf;   // (my face, HostOp::ftab row) -> row here
+    auto nbr_row = [&](int f, int old) {
+        auto it = rowOf.find({f, old});
+        if (it != rowOf.end()) return it->second;
+        std::vector<uint8_t> row(16, 0);
+        for (int s = 0; s < Nfp; s++) row[s] = (uint8_t)W.ref2dev[H.ftab[(size_t)old * Nfp + W.forder[(size_t)f * Nfp + s]]];
+        const int id = put_row(row);
+        rowOf[{f, old}] = id;
+        return id;
+    };
+
+    // ---- face descriptors ---------------------------------------------------------------------------------------------------
+    W.desc.assign((size_t)W.NEpad * 8, 0);
+    for (int e = 0; e < W.NEpad; e++)
+        for (int f = 0; f < 4; f++) {
+            int *fo = &W.desc[((size_t)e * 4 + f) * 2];
+            if (e >= NE) { fo[0] = -1; fo[1] = 0; continue; }   // boundary with BC none: zero jump
+            const int nb = H.finfo[((size_t)e * 4 + f) * 2];
+            int code = H.finfo[((size_t)e * 4 + f) * 2 + 1];
+            const int old = (code >> FI_TAB_SHIFT) & FI_TAB_MASK;
+            int row = nb >= 0 ? nbr_row(f, old) : nb == -1 ? f : 4 + f;
+            if (row > FI_TAB_MASK) throw Error(DGTD_ERR_UNSUPPORTED, "too many distinct face orientations");
+            code = (code & ~(FI_TAB_MASK << FI_TAB_SHIFT)) | (row << FI_TAB_SHIFT);
+            fo[0] = nb; fo[1] = code;
+        }
+
+    // ---- DMMA B fragments (m8n8k4: lane l holds B[k = l&3][n = l>>2]) ------------------------------------------------------
+    // Output column q of tile nt is device node 8nt + (q>>1) + 4(q&1): the accumulator pair of lane (e, j) then holds the
+    // nodes 8nt + j and 8nt + j + 4.  The last tile is "mixed": its even columns hold the node 8(NT-1) + (q>>1) of one
+    // operator and its odd columns the same node of another one, so no DMMA column is spent on padding:
+    //   volume, input component x:  even = +D_{x+2}, odd = -D_{x+1}   (k~_c = D_{c+1} u~_{c+2} - D_{c+2} u~_{c+1})
+    //   LIFT:                       even = LIFT/2,   odd = 0
+    const int VT = (NT - 1) * 3 + 3;
+    W.nfrag_vol = KSV * VT; W.nfrag_lift = Nfp * NT;
+    W.bfrag.assign((size_t)(W.nfrag_vol + W.nfrag_lift) * 32, 0.0);
+    auto D = [&](int d, int outDev, int inDev) { return H.ref.D[((size_t)d * Np + W.dev2ref[outDev]) * Np + W.dev2ref[inDev]]; };
+    for (int ks = 0; ks < KSV; ks++)
+        for (int l = 0; l < 32; l++) {
+            const int in = 4 * ks + (l & 3), q = l >> 2;
+            if (in >= Np) continue;
+            for (int nt = 0; nt < NT - 1; nt++)
+                for (int d = 0; d < 3; d++)
+                    W.bfrag[((size_t)ks * VT + nt * 3 + d) * 32 + l] = D(d, 8 * nt + (q >> 1) + 4 * (q & 1), in);
+            const int out = 8 * (NT - 1) + (q >> 1);
+            if (out < Np)
+                for (int x = 0; x < 3; x++)
+                    W.bfrag[((size_t)ks * VT + (NT - 1) * 3 + x) * 32 + l] = (q & 1) ? -D((x + 1) % 3, out, in) : D((x + 2) % 3, out, in);
+        }
+    const size_t lbase = (size_t)W.nfrag_vol * 32;
+    for (int s = 0; s < Nfp; s++)
+        for (int l = 0; l < 32; l++) {
+            const int f = l & 3, q = l >> 2, m = W.forder[(size_t)f * Nfp + s];
+            auto L = [&](int outDev) { return 0.5 * H.ref.lift[((size_t)f * Np + W.dev2ref[outDev]) * Nfp + m]; };   // the 1/2 of applyLIFT (exact)
+            for (int nt = 0; nt < NT - 1; nt++) W.bfrag[lbase + ((size_t)s * NT + nt) * 32 + l] = L(8 * nt + (q >> 1) + 4 * (q & 1));
+            const int out = 8 * (NT - 1) + (q >> 1);
+            if (out < Np && !(q & 1)) W.bfrag[lbase + ((size_t)s * NT + NT - 1) * 32 + l] = L(out);
+        }
+
+    // ---- halo pack list ---------------------------------------------------------------------------------------------------
+    W.send_off.resize(H.send_node.size());
+    for (size_t s = 0; s < H.send_node.size(); s++)
+        W.send_off[s] = ((long long)(H.send_node[s] / Np) * Np + W.ref2dev[H.send_node[s] % Np]) * 6;
+    return W;
+}
+
+}  // namespace dgtd
