@@ -474,7 +474,7 @@ int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
     c->Nloc = (long long)H.NEloc * H.Np; c->Nglob = H.NEglob * H.Np;
     c->identity = c->nranks == 1;
     for (int le = 0; le < H.NEloc && c->identity; le++) c->identity = H.elem_gid[le] == le;
-    // kernel choice: DGTD_B200_KERNEL = ws | mma | generic overrides the default (the fastest eligible one)
+    // kernel choice: DGTD_B200_KERNEL = wg | ws | mma | generic overrides the default (wg, the fastest eligible one)
     const char *kenv = std::getenv("DGTD_B200_KERNEL");
     const std::string ksel = kenv ? kenv : "";
     const char *groups = std::getenv("DGTD_B200_GROUPS");               // tuning of the mma kernel: element groups per CTA batch
@@ -483,7 +483,7 @@ int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
     for (int le = 0; le < H.NEloc; le++) has_sigma |= H.geo[(size_t)le * GEO_STRIDE + 15] != 0.0;
     c->has_sigma = has_sigma;
     const bool tabs_ok = H.ntab <= 128;
-    if (ksel == "wg" && select_wg(H.dim, H.p, c->wgs) && c->wgs.smem <= (size_t)prop.sharedMemPerBlockOptin) {
+    if ((ksel == "wg" || ksel.empty()) && select_wg(H.dim, H.p, c->wgs) && c->wgs.smem <= (size_t)prop.sharedMemPerBlockOptin) {
         c->WP = build_wg_plan(H);
         if (c->WP.ntab <= Wg<3>::TABROWS) c->blocked = c->wg = true;
     }
