@@ -147,17 +147,24 @@ static bool select_ws(int dim, int p, MmaSet &ms)
 // the warp-per-group kernel: tetrahedra of order 1..4, element-major "aos" layout, one warp per group of 8 elements
 typedef void (*WgFn)(const WgArgs);
 struct WgSet { WgFn fn[4]; int threads; size_t smem; };
-template <int P> static WgSet wgset()
+template <int P, int V, bool TF> static WgSet wgset()
 {
     using B = Wg<P>;
-    return {{stage_wg_kernel<P, 0>, stage_wg_kernel<P, 1>, stage_wg_kernel<P, 2>, stage_wg_kernel<P, 3>}, B::T, B::smem_bytes};
+    return {{stage_wg_kernel<P, 0, V, TF>, stage_wg_kernel<P, 1, V, TF>, stage_wg_kernel<P, 2, V, TF>, stage_wg_kernel<P, 3, V, TF>}, B::T, B::smem_bytes};
 }
-static bool select_wg(int dim, int p, WgSet &ws)
+template <int P> static WgSet wgset_p(int v, bool tf)
+{
+    if (v >= 3) return tf ? wgset<P, 3, true>() : wgset<P, 3, false>();
+    if (v == 2) return tf ? wgset<P, 2, true>() : wgset<P, 2, false>();
+    return tf ? wgset<P, 1, true>() : wgset<P, 1, false>();
+}
+// variants of kernels_wg.cuh: DGTD_B200_WGV=1|2 for A/B runs; tf = the context injects a TF/SF plane wave
+static bool select_wg(int dim, int p, int v, bool tf, WgSet &ws)
 {
     if (dim != 3) return false;
     switch (p) {
-        case 1: ws = wgset<1>(); return true; case 2: ws = wgset<2>(); return true;
-        case 3: ws = wgset<3>(); return true; case 4: ws = wgset<4>(); return true;
+        case 1: ws = wgset_p<1>(v, tf); return true; case 2: ws = wgset_p<2>(v, tf); return true;
+        case 3: ws = wgset_p<3>(v, tf); return true; case 4: ws = wgset_p<4>(v, tf); return true;
     }
     return false;
 }
@@ -167,6 +174,7 @@ struct dgtd_ctx {
     BlockedPlan BP;
     WgPlan WP;
     bool has_sigma = false;
+    int wgv = 1;                     // variant of the warp-per-group kernel (kernels_wg.cuh)
     bool wg = false;                 // aos layout + warp-per-group kernel (blocked is set too: state needs layout conversion)
     WgSet wgs{};
     DevBuf<uint8_t> wtab;
@@ -483,7 +491,9 @@ int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
     for (int le = 0; le < H.NEloc; le++) has_sigma |= H.geo[(size_t)le * GEO_STRIDE + 15] != 0.0;
     c->has_sigma = has_sigma;
     const bool tabs_ok = H.ntab <= 128;
-    if ((ksel == "wg" || ksel.empty()) && select_wg(H.dim, H.p, c->wgs) && c->wgs.smem <= (size_t)prop.sharedMemPerBlockOptin) {
+    const char *wgv = std::getenv("DGTD_B200_WGV");
+    c->wgv = wgv ? std::max(1, std::atoi(wgv)) : 1;
+    if ((ksel == "wg" || ksel.empty()) && select_wg(H.dim, H.p, c->wgv, H.pw.enabled && H.n_tfsf_faces > 0, c->wgs) && c->wgs.smem <= (size_t)prop.sharedMemPerBlockOptin) {
         c->WP = build_wg_plan(H);
         if (c->WP.ntab <= Wg<3>::TABROWS) c->blocked = c->wg = true;
     }
@@ -702,8 +712,8 @@ int dgtd_kernel_info(const dgtd_ctx *c, char *buf, int cap)
     if (!c || !buf || cap < 1) return fail(DGTD_ERR_ARG, "bad argument");
     char tmp[256];
     if (c->wg)
-        std::snprintf(tmp, sizeof tmp, "stage_wg_kernel<P=%d,MODE> DMMA m8n8k4 transposed, warp per group of 8 elements, aos layout, %d threads, %zu B smem, grid %d",
-                      c->H.p, c->wgs.threads, c->wgs.smem, c->grid);
+        std::snprintf(tmp, sizeof tmp, "stage_wg_kernel<P=%d,MODE,V=%d> DMMA m8n8k4 transposed, warp per group of 8 elements, aos layout, %d threads, %zu B smem, grid %d",
+                      c->H.p, c->wgv, c->wgs.threads, c->wgs.smem, c->grid);
     else if (c->blocked)
         std::snprintf(tmp, sizeof tmp, "%s<P=%d,G=%d,MODE> DMMA m8n8k4, blocked layout, %d threads, %zu B smem, grid %d",
                       c->ws ? "stage_ws_kernel" : "stage_mma_kernel", c->H.p, c->BP.G, c->ms.threads, c->ms.smem, c->grid);

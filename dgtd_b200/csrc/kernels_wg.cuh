@@ -71,18 +71,34 @@ __device__ __forceinline__ void load_rec(const double *p, double *u)
     const double2 a = q[0], b = q[1], c = q[2];
     u[0] = a.x; u[1] = a.y; u[2] = b.x; u[3] = b.y; u[4] = c.x; u[5] = c.y;
 }
+// the same as one asm-volatile statement: it keeps its place among the (volatile) DMMA statements, so a prefetch written
+// ahead of a contraction is issued ahead of it
+__device__ __forceinline__ void load_rec_pinned(const double *p, double *u)
+{
+    asm volatile("ld.v2.f64 {%0,%1}, [%6];\n\tld.v2.f64 {%2,%3}, [%6+16];\n\tld.v2.f64 {%4,%5}, [%6+32];"
+                 : "=d"(u[0]), "=d"(u[1]), "=d"(u[2]), "=d"(u[3]), "=d"(u[4]), "=d"(u[5]) : "l"(p));
+}
 __device__ __forceinline__ void store_rec(double *p, const double *u)
 {
     double2 *q = reinterpret_cast<double2 *>(p);
     q[0] = make_double2(u[0], u[1]); q[1] = make_double2(u[2], u[3]); q[2] = make_double2(u[4], u[5]);
 }
 
-template <int P, int MODE>
+// V = 0: neighbour traces prefetched one face step ahead, flux in physical components then pulled back with J^-1.
+// V >= 1: the first PF neighbour records are requested BEFORE the volume contraction (their L2 latency hides behind it),
+//        the prefetch runs PF = 2 steps ahead, and the flux is one 6x6 map per (element, face):
+//        F~_E = Ah dH + Ae dE, F~_H = -Ah dE + Ae dH with Ah = J^-1 [n x], Ae = alpha fs J^-1 (I - n n^T / fs^2).
+// V = 3: the neighbour-record loads are asm-volatile (pinned between the DMMA statements where they are written).
+// V = 2: in addition every lane whose face leaves the group pulls the neighbour's face records into L1 (prefetch.global.L1,
+//        no register, no scoreboard) as soon as the descriptors are known.
+// TF: the context has a TF/SF plane-wave source (the injection code sits in the face loop only then).
+template <int P, int MODE, int V, bool TF>
 __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
 {
     using B = Wg<P>;
     constexpr int Np = B::Np, Nfp = B::Nfp, NT = B::NT, KSV = B::KSV, VT = B::VT, GS = B::GS;
     constexpr int NL = Np - 8 * (NT - 1);                                          // nodes of the mixed tile
+    constexpr int PF = (V == 0 || P >= 4) ? 1 : 2;                                   // neighbour-record prefetch distance (face steps)
     constexpr bool LOAD_X = MODE == MODE_STAGE1 || MODE == MODE_STAGE23;           // stage 1: x == y_in, fetched again (L2 hit)
     constexpr bool LOAD_Z = MODE == MODE_STAGE23 || MODE == MODE_STAGE4;
     constexpr bool STORE_X = MODE != MODE_STAGE4, STORE_Z = MODE != MODE_MULT;      // stage 4 forms the new x in the z buffer
@@ -140,6 +156,41 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
         // The mixed tile (nt = NT-1) of field fo keeps, for input component x, the accumulator acc[3 fo + x][NT-1]:
         // element 0 -> k~_{x+1}, element 1 -> k~_{x+2} (volume); the LIFT of component c adds to acc[3 fo + (c+2)%3][NT-1][0].
 
+        // ---------------- face (e, j): where the exterior trace comes from; first neighbour records requested now ----------
+        const int2 info = wDesc[e * 4 + j];
+        const int code = info.y;
+        const double *nbase = yrec;
+        uint4 nrow = ownrow;
+        double ce = 0.0, ch = 0.0, al = A.alpha;
+        if (info.x >= 0) {
+            nrow = sTab[(code >> FI_TAB_SHIFT) & FI_TAB_MASK];
+            nbase = (info.x >> 3) == g ? wY + (info.x & 7) * Np * 6 : A.yin + (size_t)info.x * Np * 6;
+        } else if (info.x == -1) {
+            const int bc = code & FI_BC_MASK;
+            ce = bc == 1 ? -2.0 : bc == 3 ? -1.0 : 0.0;
+            ch = bc == 2 ? -2.0 : bc == 3 ? -1.0 : 0.0;
+            if (bc == 3) al = 1.0;
+        } else {
+            nrow = sTab[4 + j];
+            nbase = A.halo + (size_t)(-2 - info.x) * Nfp * 6;
+        }
+        if (V == 2 && (info.x < -1 || (info.x >= 0 && (info.x >> 3) != g))) {
+#pragma unroll
+            for (int q = 0; q < Nfp; q++) {
+                const double *r = nbase + tab_byte(nrow, q) * 6;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(r));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(r + 4));
+            }
+        }
+        double uQ[PF + 1][6];
+        if (V != 0) {
+#pragma unroll
+            for (int q = 0; q < PF; q++) {
+                if (V >= 3) load_rec_pinned(nbase + tab_byte(nrow, q) * 6, uQ[q]);
+                else load_rec(nbase + tab_byte(nrow, q) * 6, uQ[q]);
+            }
+        }
+
         // ---------------- volume: k~E_c = D_{c+1} u~H_{c+2} - D_{c+2} u~H_{c+1},  k~H likewise from u~E = -J^T E / det ------
         {
             double jm[9];
@@ -182,23 +233,6 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
 
         // ---------------- face flux of (element e, face j) -> LIFT --------------------------------------------------------
         {
-            const int2 info = wDesc[e * 4 + j];
-            const int code = info.y;
-            const double *nbase = yrec;
-            uint4 nrow = ownrow;
-            double ce = 0.0, ch = 0.0, al = A.alpha;
-            if (info.x >= 0) {
-                nrow = sTab[(code >> FI_TAB_SHIFT) & FI_TAB_MASK];
-                nbase = (info.x >> 3) == g ? wY + (info.x & 7) * Np * 6 : A.yin + (size_t)info.x * Np * 6;
-            } else if (info.x == -1) {
-                const int bc = code & FI_BC_MASK;
-                ce = bc == 1 ? -2.0 : bc == 3 ? -1.0 : 0.0;
-                ch = bc == 2 ? -2.0 : bc == 3 ? -1.0 : 0.0;
-                if (bc == 3) al = 1.0;
-            } else {
-                nrow = sTab[4 + j];
-                nbase = A.halo + (size_t)(-2 - info.x) * Nfp * 6;
-            }
             const int tf = (code >> FI_TFSF_SHIFT) & FI_TFSF_MASK;
             double ji[9];
 #pragma unroll
@@ -209,16 +243,34 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
             const double fs = ge[18 + j];
             const double ifs = 1.0 / fs, ifs2 = ifs * ifs;
             const double af = al * fs;
-            double uP[6];
-            load_rec(nbase + tab_byte(nrow, 0) * 6, uP);
+            double Ah[9], Ae[9];
+            if (V != 0) {
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    const double j0 = ji[3 * a], j1 = ji[3 * a + 1], j2 = ji[3 * a + 2];
+                    Ah[3 * a + 0] = j1 * gn[2] - j2 * gn[1];
+                    Ah[3 * a + 1] = j2 * gn[0] - j0 * gn[2];
+                    Ah[3 * a + 2] = j0 * gn[1] - j1 * gn[0];
+                    const double w = (j0 * gn[0] + j1 * gn[1] + j2 * gn[2]) * ifs2;
+                    Ae[3 * a + 0] = af * (j0 - w * gn[0]);
+                    Ae[3 * a + 1] = af * (j1 - w * gn[1]);
+                    Ae[3 * a + 2] = af * (j2 - w * gn[2]);
+                }
+            } else {
+                load_rec(nbase + tab_byte(nrow, 0) * 6, uQ[0]);
+            }
 #pragma unroll
             for (int s = 0; s < Nfp; s++) {
-                double uM[6], uN[6], dU[6];
+                double uM[6], dU[6];
+                const double *uP = uQ[s % (PF + 1)];
                 load_rec(yrec + tab_byte(ownrow, s) * 6, uM);
-                if (s + 1 < Nfp) load_rec(nbase + tab_byte(nrow, s + 1) * 6, uN);
+                if (s + PF < Nfp) {
+                    if (V >= 3) load_rec_pinned(nbase + tab_byte(nrow, s + PF) * 6, uQ[(s + PF) % (PF + 1)]);
+                    else load_rec(nbase + tab_byte(nrow, s + PF) * 6, uQ[(s + PF) % (PF + 1)]);
+                }
 #pragma unroll
                 for (int c = 0; c < 3; c++) { dU[c] = fma(ce, uM[c], uP[c] - uM[c]); dU[3 + c] = fma(ch, uM[3 + c], uP[3 + c] - uM[3 + c]); }
-                if (tf && inject) {
+                if (TF && tf && inject) {
                     double inc[6];
                     const int m = tab_byte(sTab[4 + j], s);
                     planewave6(A.pw, A.tfsf_xyz + ((long long)(code >> FI_TIDX_SHIFT) * Nfp + m) * 3, A.t, inc);
@@ -226,20 +278,30 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
 #pragma unroll
                     for (int c = 0; c < 6; c++) dU[c] += sg * inc[c];
                 }
-                const double gdE = (gn[0] * dU[0] + gn[1] * dU[1] + gn[2] * dU[2]) * ifs2;
-                const double gdH = (gn[0] * dU[3] + gn[1] * dU[4] + gn[2] * dU[5]) * ifs2;
-                double fl[6];
-                fl[0] = (gn[1] * dU[5] - gn[2] * dU[4]) + af * (dU[0] - gdE * gn[0]);
-                fl[1] = (gn[2] * dU[3] - gn[0] * dU[5]) + af * (dU[1] - gdE * gn[1]);
-                fl[2] = (gn[0] * dU[4] - gn[1] * dU[3]) + af * (dU[2] - gdE * gn[2]);
-                fl[3] = -(gn[1] * dU[2] - gn[2] * dU[1]) + af * (dU[3] - gdH * gn[0]);
-                fl[4] = -(gn[2] * dU[0] - gn[0] * dU[2]) + af * (dU[4] - gdH * gn[1]);
-                fl[5] = -(gn[0] * dU[1] - gn[1] * dU[0]) + af * (dU[5] - gdH * gn[2]);
                 double ft[6];
+                if (V != 0) {
 #pragma unroll
-                for (int a = 0; a < 3; a++) {
-                    ft[a] = fma(ji[3 * a], fl[0], fma(ji[3 * a + 1], fl[1], ji[3 * a + 2] * fl[2]));
-                    ft[3 + a] = fma(ji[3 * a], fl[3], fma(ji[3 * a + 1], fl[4], ji[3 * a + 2] * fl[5]));
+                    for (int a = 0; a < 3; a++) {
+                        ft[a] = fma(Ae[3 * a + 2], dU[2], fma(Ae[3 * a + 1], dU[1], fma(Ae[3 * a], dU[0],
+                                fma(Ah[3 * a + 2], dU[5], fma(Ah[3 * a + 1], dU[4], Ah[3 * a] * dU[3])))));
+                        ft[3 + a] = fma(Ae[3 * a + 2], dU[5], fma(Ae[3 * a + 1], dU[4], fma(Ae[3 * a], dU[3],
+                                    -fma(Ah[3 * a + 2], dU[2], fma(Ah[3 * a + 1], dU[1], Ah[3 * a] * dU[0])))));
+                    }
+                } else {
+                    const double gdE = (gn[0] * dU[0] + gn[1] * dU[1] + gn[2] * dU[2]) * ifs2;
+                    const double gdH = (gn[0] * dU[3] + gn[1] * dU[4] + gn[2] * dU[5]) * ifs2;
+                    double fl[6];
+                    fl[0] = (gn[1] * dU[5] - gn[2] * dU[4]) + af * (dU[0] - gdE * gn[0]);
+                    fl[1] = (gn[2] * dU[3] - gn[0] * dU[5]) + af * (dU[1] - gdE * gn[1]);
+                    fl[2] = (gn[0] * dU[4] - gn[1] * dU[3]) + af * (dU[2] - gdE * gn[2]);
+                    fl[3] = -(gn[1] * dU[2] - gn[2] * dU[1]) + af * (dU[3] - gdH * gn[0]);
+                    fl[4] = -(gn[2] * dU[0] - gn[0] * dU[2]) + af * (dU[4] - gdH * gn[1]);
+                    fl[5] = -(gn[0] * dU[1] - gn[1] * dU[0]) + af * (dU[5] - gdH * gn[2]);
+#pragma unroll
+                    for (int a = 0; a < 3; a++) {
+                        ft[a] = fma(ji[3 * a], fl[0], fma(ji[3 * a + 1], fl[1], ji[3 * a + 2] * fl[2]));
+                        ft[3 + a] = fma(ji[3 * a], fl[3], fma(ji[3 * a + 1], fl[4], ji[3 * a + 2] * fl[5]));
+                    }
                 }
                 const double *fr = sFragL + (s * NT) * 32 + lane;
 #pragma unroll
@@ -255,10 +317,6 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
                         const int xa = 3 * (c / 3) + (c % 3 + 2) % 3;
                         dmma884(acc[xa][NT - 1][0], acc[xa][NT - 1][1], ft[c], bv);
                     }
-                }
-                if (s + 1 < Nfp) {
-#pragma unroll
-                    for (int c = 0; c < 6; c++) uP[c] = uN[c];
                 }
             }
         }
