@@ -250,7 +250,7 @@ def main():
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(n_gpus, cubes), "dofs_per_gpu": 6 * nloc, "dt": dt,
                            "l2": "inputs (4 x %.0f MB per GPU) are larger than L2, no flush" % (6 * nloc * 8 / 1e6),
-                           "halo_bytes_per_rhs": ev.halo_bytes(), "state_norm": float(norm2.sqrt().item())},
+                           "halo_bytes_per_rhs": ev.halo_bytes(), "halo": {0: "none", 1: "nccl send/recv", 2: "peer-memory stores fused into the stage kernel"}[ev.halo_mode()], "state_norm": float(norm2.sqrt().item())},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                              "traffic": ncu_traffic(ev.kernel_info(), 6 * nloc), "peak_source": how,
                              "alg_bytes_per_dof_update": B_ALG[ORDER], "alg_bytes_per_launch": alg_bytes,

@@ -59,6 +59,7 @@ def _load():
     L.dgtd_launch_count.restype = C.c_longlong
     L.dgtd_launch_count.argtypes = [C.c_void_p]
     L.dgtd_kernel_info.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    L.dgtd_halo_mode.argtypes = [C.c_void_p]
     L.dgtd_mesh_destroy.restype = None
     L.dgtd_mesh_destroy.argtypes = [C.c_void_p]
     L.dgtd_destroy.restype = None
@@ -278,14 +279,18 @@ class Evolution:
         return lib.dgtd_launch_count(self._h)
 
     def kernel_info(self):
-        buf = C.create_string_buffer(256)
-        _ck(lib.dgtd_kernel_info(self._h, buf, 256))
+        buf = C.create_string_buffer(320)
+        _ck(lib.dgtd_kernel_info(self._h, buf, 320))
         return buf.value.decode()
 
     def halo_bytes(self):
         b = C.c_longlong()
         _ck(lib.dgtd_halo_bytes(self._h, C.byref(b)))
         return b.value
+
+    def halo_mode(self):
+        """0 single rank, 1 NCCL send/recv, 2 peer-memory stores fused into the stage kernel (DGTD_HALO_*)."""
+        return lib.dgtd_halo_mode(self._h)
 
     def comm_init(self, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, 128)

@@ -54,6 +54,8 @@ struct Nccl {
     int (*GroupEnd)() = nullptr;
     int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
     void load()
     {
@@ -68,12 +70,15 @@ struct Nccl {
         GroupEnd = (decltype(GroupEnd))sym("ncclGroupEnd");
         Send = (decltype(Send))sym("ncclSend");
         Recv = (decltype(Recv))sym("ncclRecv");
+        AllGather = (decltype(AllGather))sym("ncclAllGather");
+        AllReduce = (decltype(AllReduce))sym("ncclAllReduce");
         GetErrorString = (decltype(GetErrorString))sym("ncclGetErrorString");
     }
     void check(int r, const char *what) { if (r != 0) throw Error(DGTD_ERR_COMM, std::string(what) + ": " + (GetErrorString ? GetErrorString(r) : "nccl error")); }
 };
 Nccl g_nccl;
 constexpr int NCCL_FLOAT64 = 8;   // ncclDouble
+constexpr int NCCL_UINT8 = 1, NCCL_INT32 = 2, NCCL_MIN = 3;
 }  // namespace
 
 template <class T> struct DevBuf {
@@ -155,7 +160,6 @@ template <int P, int V, bool TF> static WgSet wgset()
 template <int P> static WgSet wgset_p(int v, bool tf)
 {
     if (v >= 3) return tf ? wgset<P, 3, true>() : wgset<P, 3, false>();
-    if (v == 2) return tf ? wgset<P, 2, true>() : wgset<P, 2, false>();
     return tf ? wgset<P, 1, true>() : wgset<P, 1, false>();
 }
 // variants of kernels_wg.cuh: DGTD_B200_WGV=1|2 for A/B runs; tf = the context injects a TF/SF plane wave
@@ -200,10 +204,22 @@ struct dgtd_ctx {
     DevPlaneWave pw{};
     int pw_on = 0;
     ncclComm_t comm = nullptr;
+    // direct halo exchange over peer memory (kernels_wg.cuh: WgP2P).  p2p_mem = [4 KB flags][halo buffer 0][halo buffer 1]
+    bool p2p = false;
+    DevBuf<unsigned char> p2p_mem;
+    size_t p2p_hb = 0;                               // bytes of one halo buffer (128-byte multiple)
+    void *p2p_peer_base[P2P_MAXPEERS] = {};          // peers' p2p_mem, mapped with cudaIpcOpenMemHandle
+    size_t p2p_peer_hb[P2P_MAXPEERS] = {};
+    unsigned long long epoch = 0;                    // exchanges produced so far (all ranks run the same sequence)
+    const double *pushed = nullptr;                  // vector whose traces exchange `epoch` carries (nullptr: none valid)
+    DevBuf<unsigned int> p2p_done;
+    DevBuf<int> p2p_err;
+    DevBuf<int> hpush;
     long long launches = 0;
     std::vector<double> hostbuf;     // pinned staging would go here; plain vector for gather/scatter by element
     ~dgtd_ctx()
     {
+        for (void *b : p2p_peer_base) if (b) cudaIpcCloseMemHandle(b);
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
         if (own_stream) cudaStreamDestroy(own_stream);
     }
@@ -249,6 +265,72 @@ static void exchange(dgtd_ctx *c, const double *y)
     g_nccl.check(g_nccl.GroupEnd(), "ncclGroupEnd");
 }
 
+// Peer-memory halo path of the warp-per-group kernel: every rank exports [flags | halo 0 | halo 1] with CUDA IPC, the
+// handles travel through one ncclAllGather, every rank maps its neighbours' buffers.  All ranks must agree (ncclAllReduce
+// min) or all stay on the NCCL send/recv path.  DGTD_B200_HALO=nccl forces the latter.
+static void p2p_setup(dgtd_ctx *c)
+{
+    struct Card { cudaIpcMemHandle_t h; unsigned long long hb; unsigned long long ok; char pad[128 - sizeof(cudaIpcMemHandle_t) - 16]; };
+    static_assert(sizeof(Card) == 128, "card size");
+    const char *env = std::getenv("DGTD_B200_HALO");
+    int want = c->wg && c->nranks <= 512 && (int)c->H.peers.size() <= P2P_MAXPEERS && !(env && std::string(env) == "nccl");
+    Card mine{};
+    if (want) {
+        c->p2p_hb = (((size_t)c->H.n_halo_faces * c->H.Nfp * 6 * sizeof(double)) + 127) / 128 * 128;
+        c->p2p_mem.alloc(4096 + 2 * c->p2p_hb + 128);
+        CU(cudaMemset(c->p2p_mem.p, 0, c->p2p_mem.n));
+        c->p2p_done.alloc(1); c->p2p_err.alloc(1);
+        CU(cudaMemset(c->p2p_done.p, 0, sizeof(unsigned int))); CU(cudaMemset(c->p2p_err.p, 0, sizeof(int)));
+        if (cudaIpcGetMemHandle(&mine.h, c->p2p_mem.p) != cudaSuccess) { cudaGetLastError(); want = 0; }
+        mine.hb = c->p2p_hb;
+    }
+    mine.ok = (unsigned long long)want;
+    DevBuf<unsigned char> dsend, drecv;
+    dsend.alloc(sizeof(Card)); drecv.alloc(sizeof(Card) * (size_t)c->nranks);
+    CU(cudaMemcpyAsync(dsend.p, &mine, sizeof(Card), cudaMemcpyHostToDevice, c->stream));
+    g_nccl.check(g_nccl.AllGather(dsend.p, drecv.p, sizeof(Card), NCCL_UINT8, c->comm, c->stream), "ncclAllGather");
+    std::vector<Card> all((size_t)c->nranks);
+    CU(cudaMemcpyAsync(all.data(), drecv.p, sizeof(Card) * (size_t)c->nranks, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    int ok = want;
+    for (auto &cd : all) ok &= (int)cd.ok;
+    if (ok)
+        for (size_t p = 0; p < c->H.peers.size(); p++) {
+            const Card &cd = all[(size_t)c->H.peers[p].rank];
+            if (cudaIpcOpenMemHandle(&c->p2p_peer_base[p], cd.h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); c->p2p_peer_base[p] = nullptr; ok = 0; break; }
+            c->p2p_peer_hb[p] = (size_t)cd.hb;
+        }
+    // collective verdict
+    DevBuf<int> dflag; dflag.alloc(1);
+    CU(cudaMemcpyAsync(dflag.p, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    g_nccl.check(g_nccl.AllReduce(dflag.p, dflag.p, 1, NCCL_INT32, NCCL_MIN, c->comm, c->stream), "ncclAllReduce");
+    CU(cudaMemcpyAsync(&ok, dflag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (!ok) {
+        for (void *&b : c->p2p_peer_base) if (b) { cudaIpcCloseMemHandle(b); b = nullptr; }
+        c->p2p = false;
+        return;
+    }
+    c->p2p = true; c->epoch = 0; c->pushed = nullptr;
+}
+// all ranks' kernels must have drained before any rank unmaps or frees a halo buffer its neighbours store into
+static void p2p_quiesce(dgtd_ctx *c)
+{
+    if (!c->p2p || !c->comm) return;
+    cudaStreamSynchronize(c->stream);
+    DevBuf<int> d; d.alloc(1);
+    cudaMemsetAsync(d.p, 0, sizeof(int), c->stream);
+    g_nccl.AllReduce(d.p, d.p, 1, NCCL_INT32, NCCL_MIN, c->comm, c->stream);
+    cudaStreamSynchronize(c->stream);
+}
+static void p2p_check(dgtd_ctx *c)
+{
+    if (!c->p2p) return;
+    int e = 0;
+    CU(cudaMemcpy(&e, c->p2p_err.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e) throw Error(DGTD_ERR_COMM, "halo exchange: a neighbour rank did not signal within 20 s");
+}
+
 static void launch_gate(dgtd_ctx *c, const double *ts, int nt)
 {
     CU(cudaMemsetAsync(c->gate.p, 0, 4 * sizeof(double), c->stream));
@@ -257,11 +339,48 @@ static void launch_gate(dgtd_ctx *c, const double *ts, int nt)
     c->launches++;
 }
 
+// WgP2P of one launch: consume exchange `wait` from my halo buffers, produce exchange `signal` into the peers'
+static WgP2P p2p_args(dgtd_ctx *c, unsigned long long wait, unsigned long long signal)
+{
+    WgP2P q{};
+    if (!c->p2p) return q;
+    q.hpush = reinterpret_cast<const int2 *>(c->hpush.p);
+    q.npeers = (int)c->H.peers.size();
+    q.flags = reinterpret_cast<const unsigned long long *>(c->p2p_mem.p);
+    for (int p = 0; p < q.npeers; p++) {
+        unsigned char *base = static_cast<unsigned char *>(c->p2p_peer_base[p]);
+        q.peer_out[p] = reinterpret_cast<double *>(base + 4096 + (signal & 1) * c->p2p_peer_hb[p]);
+        q.peer_flag[p] = reinterpret_cast<unsigned long long *>(base) + c->H.peers[p].remote_idx;
+    }
+    q.wait_epoch = wait; q.signal_epoch = signal;
+    q.done = c->p2p_done.p; q.err = c->p2p_err.p;
+    return q;
+}
+static const double *p2p_halo_in(dgtd_ctx *c, unsigned long long k)
+{
+    return reinterpret_cast<const double *>(c->p2p_mem.p + 4096 + (k & 1) * c->p2p_hb);
+}
+
 static void launch_stage(dgtd_ctx *c, int mode, StageArgs &A)
 {
-    exchange(c, A.yin);
+    const bool p2p = c->p2p && c->H.n_halo_faces > 0;
+    if (p2p) {
+        if (c->pushed != A.yin) {   // the traces of y_in are not at the peers yet: stand-alone producer of the next exchange
+            const int nrec = c->H.n_halo_faces * c->H.Nfp;
+            c->epoch++;
+            halo_push_kernel<<<std::min(296, (nrec + 127) / 128), 128, 0, c->stream>>>(A.yin, c->bsend_off.p, nrec, c->H.Nfp, p2p_args(c, 0, c->epoch));
+            c->launches++;
+            c->pushed = A.yin;
+        }
+    } else exchange(c, A.yin);
     if (c->wg) {
         WgArgs W;
+        W.pp = p2p_args(c, 0, 0);
+        if (p2p) {
+            A.halo = p2p_halo_in(c, c->epoch);
+            if (mode != MODE_MULT) { W.pp = p2p_args(c, c->epoch, c->epoch + 1); c->epoch++; c->pushed = A.yout; }
+            else W.pp = p2p_args(c, c->epoch, 0);
+        }
         W.bfrag = c->bafrag.p; W.geo = c->bgeo.p; W.desc = c->bdesc.p; W.tab = c->wtab.p; W.ntab = c->WP.ntab;
         W.tfsf_xyz = A.tfsf_xyz; W.gate = A.gate; W.halo = A.halo; W.ngroups = c->WP.ngroups; W.has_sigma = c->has_sigma ? 1 : 0;
         W.alpha = A.alpha; W.pw = A.pw; W.pw_on = A.pw_on;
@@ -327,6 +446,7 @@ static void from_device_layout(dgtd_ctx *c, const double *dev, double *ref)
 static void upload_local(dgtd_ctx *c, const double *hloc, double *dev)
 {
     const long long Nl = c->Nloc;
+    if (c->pushed == dev) c->pushed = nullptr;
     if (!c->blocked) {
         CU(cudaMemcpyAsync(dev, hloc, sizeof(double) * 6 * Nl, cudaMemcpyHostToDevice, c->stream));
     } else {
@@ -339,6 +459,7 @@ static void upload_local(dgtd_ctx *c, const double *hloc, double *dev)
 static void download_local(dgtd_ctx *c, const double *dev, double *hloc)
 {
     const long long Nl = c->Nloc;
+    p2p_check(c);
     if (!c->blocked) {
         CU(cudaMemcpyAsync(hloc, dev, sizeof(double) * 6 * Nl, cudaMemcpyDeviceToHost, c->stream));
     } else {
@@ -503,7 +624,7 @@ int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
         const int nw = c->wgs.threads / 32;
         c->grid = (int)std::min<long long>(((long long)c->WP.ngroups + nw - 1) / nw, (long long)prop.multiProcessorCount);
         c->bgeo.upload(c->WP.geo); c->bafrag.upload(c->WP.bfrag); c->bdesc.upload(c->WP.desc); c->bsend_off.upload(c->WP.send_off, 1);
-        c->wtab.upload(c->WP.tab, 16); c->dev2ref.upload(c->WP.dev2ref);
+        c->wtab.upload(c->WP.tab, 16); c->dev2ref.upload(c->WP.dev2ref); c->hpush.upload(c->WP.hpush, 2);
     } else if (ksel != "generic" && tabs_ok) {
         if (ksel != "mma" && !has_sigma && select_ws(H.dim, H.p, c->ms) && c->ms.smem <= (size_t)prop.sharedMemPerBlockOptin) { c->blocked = c->ws = true; G = 2; }
         else if (select_mma(H.dim, H.p, G, c->ms) || select_mma(H.dim, H.p, G = 1, c->ms)) c->blocked = c->ms.smem <= (size_t)prop.sharedMemPerBlockOptin;
@@ -563,6 +684,7 @@ void dgtd_destroy(dgtd_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    p2p_quiesce(c);
     delete c;
 }
 int dgtd_sizes(const dgtd_ctx *c, long long *n_global, int *np, long long *ne_local, long long *n_local)
@@ -627,6 +749,7 @@ int dgtd_state_device_ptr(dgtd_ctx *c, double **dev)
 {
     if (!c || !dev) return fail(DGTD_ERR_ARG, "null argument");
     *dev = c->x.p;
+    c->pushed = nullptr;      // the caller may write the state behind our back
     return DGTD_OK;
 }
 int dgtd_mult(dgtd_ctx *c, double t, const double *in, double *out, int on_device)
@@ -635,6 +758,7 @@ int dgtd_mult(dgtd_ctx *c, double t, const double *in, double *out, int on_devic
     if (!c || !in || !out) throw Error(DGTD_ERR_ARG, "null argument");
     CU(cudaSetDevice(c->device));
     const size_t n6 = (size_t)6 * c->Nalloc;
+    c->pushed = nullptr;   // tmp_in / a caller-owned vector is about to change under the same address
     if (on_device && !c->blocked) { mult_device(c, t, in, out); }
     else {
         if (c->tmp_in.n != n6) { c->tmp_in.alloc(n6); c->tmp_out.alloc(n6); }
@@ -704,16 +828,17 @@ int dgtd_synchronize(dgtd_ctx *c)
     if (!c) throw Error(DGTD_ERR_ARG, "null context");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
+    p2p_check(c);
     GUARD_END
 }
 long long dgtd_launch_count(const dgtd_ctx *c) { return c ? c->launches : 0; }
 int dgtd_kernel_info(const dgtd_ctx *c, char *buf, int cap)
 {
     if (!c || !buf || cap < 1) return fail(DGTD_ERR_ARG, "bad argument");
-    char tmp[256];
+    char tmp[320];
     if (c->wg)
-        std::snprintf(tmp, sizeof tmp, "stage_wg_kernel<P=%d,MODE,V=%d> DMMA m8n8k4 transposed, warp per group of 8 elements, aos layout, %d threads, %zu B smem, grid %d",
-                      c->H.p, c->wgv, c->wgs.threads, c->wgs.smem, c->grid);
+        std::snprintf(tmp, sizeof tmp, "stage_wg_kernel<P=%d,MODE,V=%d> DMMA m8n8k4 transposed, warp per group of 8 elements, aos layout, %d threads, %zu B smem, grid %d%s",
+                      c->H.p, c->wgv, c->wgs.threads, c->wgs.smem, c->grid, c->nranks == 1 ? "" : c->p2p ? ", halo: fused peer-memory stores" : ", halo: NCCL send/recv");
     else if (c->blocked)
         std::snprintf(tmp, sizeof tmp, "%s<P=%d,G=%d,MODE> DMMA m8n8k4, blocked layout, %d threads, %zu B smem, grid %d",
                       c->ws ? "stage_ws_kernel" : "stage_mma_kernel", c->H.p, c->BP.G, c->ms.threads, c->ms.smem, c->grid);
@@ -747,6 +872,17 @@ int dgtd_setup_query(const dgtd_mesh *mesh, const dgtd_options *o, const char *n
     else if (n == "tfsf_side") { src = H.tfsf_side.data(); bytes = H.tfsf_side.size() * 4; }
     else if (n == "send_node") { src = H.send_node.data(); bytes = H.send_node.size() * 4; }
     else if (n == "peers") { for (auto &p : H.peers) { dims.push_back(p.rank); dims.push_back(p.nfaces); dims.push_back(p.send_off); } src = dims.data(); bytes = dims.size() * 4; }
+    else if (n == "peers5") { for (auto &p : H.peers) { dims.push_back(p.rank); dims.push_back(p.nfaces); dims.push_back(p.send_off); dims.push_back(p.remote_off); dims.push_back(p.remote_idx); } src = dims.data(); bytes = dims.size() * 4; }
+    else if (n.rfind("wg_", 0) == 0) {   // tables of the warp-per-group kernel's plan (tetrahedra)
+        static thread_local WgPlan WP;
+        WP = build_wg_plan(H);
+        if (n == "wg_hpush") { src = WP.hpush.data(); bytes = WP.hpush.size() * 4; }
+        else if (n == "wg_tab") { src = WP.tab.data(); bytes = WP.tab.size(); }
+        else if (n == "wg_desc") { src = WP.desc.data(); bytes = WP.desc.size() * 4; }
+        else if (n == "wg_send_off") { src = WP.send_off.data(); bytes = WP.send_off.size() * 8; }
+        else if (n == "wg_dev2ref") { src = WP.dev2ref.data(); bytes = WP.dev2ref.size() * 4; }
+        else throw Error(DGTD_ERR_ARG, "unknown setup table " + n);
+    }
     else if (n == "dims") { dims = {H.dim, H.p, H.Np, H.Nfp, H.nf, H.NEloc, H.ntab, H.n_tfsf_faces, H.n_halo_faces}; src = dims.data(); bytes = dims.size() * 4; }
     else if (n == "node_coords") { node_coords(mesh->m, H.ref, xyz); src = xyz.data(); bytes = xyz.size() * 8; }
     else if (n.rfind("blk_", 0) == 0) {   // tables of the DMMA kernel's plan (tetrahedra), one group per batch
@@ -783,7 +919,14 @@ int dgtd_comm_init(dgtd_ctx *c, const void *id128)
     g_nccl.load();
     NcclId id; std::memcpy(&id, id128, 128);
     g_nccl.check(g_nccl.CommInitRank(&c->comm, c->nranks, id, c->rank), "ncclCommInitRank");
+    p2p_setup(c);
     GUARD_END
+}
+int dgtd_halo_mode(const dgtd_ctx *c)
+{
+    if (!c) return -1;
+    if (c->nranks == 1) return DGTD_HALO_NONE;
+    return c->p2p ? DGTD_HALO_P2P : DGTD_HALO_NCCL;
 }
 int dgtd_halo_bytes(const dgtd_ctx *c, long long *bytes)
 {

@@ -75,6 +75,8 @@ struct PeerPlan {
     int rank = -1;
     int nfaces = 0;
     int send_off = 0, recv_off = 0;      // in faces, into the packed send list / the halo slots
+    int remote_off = 0;                  // first halo slot of MY block on the peer (its recv_off for me)
+    int remote_idx = 0;                  // my position in the peer's peer list
 };
 
 // Everything a rank uploads to its GPU.
@@ -141,6 +143,7 @@ struct WgPlan {
     int ntab = 0;
     std::vector<double> bfrag;         // (nfrag_vol + nfrag_lift) * 32
     std::vector<long long> send_off;   // nSendFaces*Nfp : offset (doubles) of the node record in the aos state
+    std::vector<int> hpush;            // nHaloFaces*2 : {peer index | tab row << 8 (own device node per RECEIVER face node), slot on the peer}
 };
 WgPlan build_wg_plan(const HostOp &H);
 void node_coords(const Mesh &m, const RefElem &ref, std::vector<double> &xyz);   // [NE*Np][3], global numbering

@@ -23,6 +23,65 @@
 
 namespace dgtd {
 
+// Direct halo exchange over NVLink peer memory (one process per GPU, buffers mapped with CUDA IPC): the stage kernel that
+// PRODUCES y_out stores the traces of its partition faces straight into the neighbour rank's halo buffer, and the kernel
+// that CONSUMES them waits, only in the warps that own a partition face, for the neighbour's epoch flag.  Exchange number k
+// uses halo buffer k & 1 on every rank; a rank signals k after ALL its stores of exchange k (last-CTA election), which is
+// also after its reads of exchange k-1, so two buffers are enough (see capi.cu: p2p_* for the host side).
+// Replaces GlobalEvolution.cpp:763-774 (six blocking MPI exchanges of whole neighbour elements per Mult).
+constexpr int P2P_MAXPEERS = 8;
+struct WgP2P {
+    const int2 *hpush;                                   // WgPlan::hpush
+    double *peer_out[P2P_MAXPEERS];                      // peer's halo buffer of the exchange being produced
+    unsigned long long *peer_flag[P2P_MAXPEERS];         // peer's flag slot for this rank
+    const unsigned long long *flags;                     // my flag slots, one per peer
+    int npeers;
+    unsigned long long wait_epoch, signal_epoch;         // 0: nothing to wait for / nothing to produce
+    unsigned int *done;                                  // CTA counter of the last-CTA election
+    int *err;                                            // set when a wait timed out
+};
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// lanes 0..npeers-1 of the calling warp wait for their peer's flag; 20 s without progress sets *err and gives up
+__device__ __forceinline__ void p2p_wait(const WgP2P &pp, int lane)
+{
+    if (lane < pp.npeers) {
+        const unsigned long long t0 = globaltimer_ns();
+        while (ld_acquire_sys(pp.flags + lane) < pp.wait_epoch) {
+            if (globaltimer_ns() - t0 > 20000000000ull) { atomicExch(pp.err, 1); break; }
+        }
+    }
+    __syncwarp();
+}
+// after the last store of the CTA: make them visible system-wide, elect the last CTA of the grid, signal every peer
+__device__ __forceinline__ void p2p_signal(const WgP2P &pp)
+{
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(pp.done, 1u);
+        if (prev == gridDim.x - 1) {
+            *pp.done = 0;
+            __threadfence_system();
+            for (int p = 0; p < pp.npeers; p++) st_release_sys(pp.peer_flag[p], pp.signal_epoch);
+        }
+    }
+}
+
 struct WgArgs {
     const double *bfrag;      // WgPlan::bfrag
     const double *geo;        // [NEpad][32]
@@ -40,6 +99,7 @@ struct WgArgs {
     const double *yin, *x;    // aos layout
     double *z, *yout;
     double a, b, t;
+    WgP2P pp;
 };
 
 template <int P> struct Wg {
@@ -88,9 +148,8 @@ __device__ __forceinline__ void store_rec(double *p, const double *u)
 // V >= 1: the first PF neighbour records are requested BEFORE the volume contraction (their L2 latency hides behind it),
 //        the prefetch runs PF = 2 steps ahead, and the flux is one 6x6 map per (element, face):
 //        F~_E = Ah dH + Ae dE, F~_H = -Ah dE + Ae dH with Ah = J^-1 [n x], Ae = alpha fs J^-1 (I - n n^T / fs^2).
-// V = 3: the neighbour-record loads are asm-volatile (pinned between the DMMA statements where they are written).
-// V = 2: in addition every lane whose face leaves the group pulls the neighbour's face records into L1 (prefetch.global.L1,
-//        no register, no scoreboard) as soon as the descriptors are known.
+// V = 3: the neighbour-record loads are asm-volatile (pinned between the DMMA statements where they are written); measured
+//        equal to V = 1.  (Pulling the neighbour records into L1 with prefetch.global.L1 was measured 9 % slower.)
 // TF: the context has a TF/SF plane-wave source (the injection code sits in the face loop only then).
 template <int P, int MODE, int V, bool TF>
 __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
@@ -125,7 +184,8 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
 
     const int gstride = gridDim.x * B::NW;
     int g = blockIdx.x * B::NW + warp;
-    if (g >= A.ngroups) return;
+    const bool has_work = g < A.ngroups;
+    bool halo_ready = A.pp.wait_epoch == 0;
     const uint4 ownrow = sTab[j];
     const bool inject = A.pw_on && (A.gate == nullptr || *A.gate >= 1e-16);
 
@@ -140,7 +200,7 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
         if (LOAD_X) bulk_load(wX, (MODE == MODE_STAGE1 ? A.yin : A.x) + (size_t)gg * GS, GS * 8, barXZ);
         if (LOAD_Z) bulk_load(wZ, A.z + (size_t)gg * GS, GS * 8, barXZ);
     };
-    if (lane == 0) { issue_y(g); if (LOAD_X || LOAD_Z) issue_xz(g); }
+    if (lane == 0 && has_work) { issue_y(g); if (LOAD_X || LOAD_Z) issue_xz(g); }
 
     for (int it = 0; g < A.ngroups; g += gstride, it++) {
         const uint32_t par = it & 1;
@@ -174,14 +234,7 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
             nrow = sTab[4 + j];
             nbase = A.halo + (size_t)(-2 - info.x) * Nfp * 6;
         }
-        if (V == 2 && (info.x < -1 || (info.x >= 0 && (info.x >> 3) != g))) {
-#pragma unroll
-            for (int q = 0; q < Nfp; q++) {
-                const double *r = nbase + tab_byte(nrow, q) * 6;
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(r));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(r + 4));
-            }
-        }
+        if (!halo_ready && __any_sync(0xffffffffu, info.x < -1)) { p2p_wait(A.pp, lane); halo_ready = true; }
         double uQ[PF + 1][6];
         if (V != 0) {
 #pragma unroll
@@ -379,6 +432,18 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
             }
         fence_async_smem();
         __syncwarp();
+        if (MODE != MODE_MULT && A.pp.signal_epoch != 0 && info.x < -1) {   // my traces of the new stage vector -> the peer's halo
+            const int2 hp = A.pp.hpush[-2 - info.x];
+            const uint4 prow = sTab[hp.x >> 8];
+            double *dst = A.pp.peer_out[hp.x & 0xff] + (size_t)hp.y * Nfp * 6;
+            const double *src = (MODE == MODE_STAGE4 ? wZ : wX) + e * Np * 6;
+#pragma unroll
+            for (int m = 0; m < Nfp; m++) {
+                double r[6];
+                load_rec(src + tab_byte(prow, m) * 6, r);
+                store_rec(dst + m * 6, r);
+            }
+        }
         if (lane == 0) {
             const size_t goff = (size_t)g * GS;
             if (STORE_X) bulk_store(A.yout + goff, wX, GS * 8);
@@ -391,6 +456,21 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
         __syncwarp();
     }
     if (lane == 0) bulk_wait_all();
+    if (MODE != MODE_MULT && A.pp.signal_epoch != 0) p2p_signal(A.pp);
+}
+
+// Stand-alone producer of an exchange (the state came from the host, or Mult was called on a foreign vector): the traces of
+// `y` (aos layout) go to the peers' halo buffers, then the same last-CTA signal.
+__global__ void halo_push_kernel(const double *y, const long long *send_off, int nrec, int Nfp, const WgP2P pp)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nrec; i += gridDim.x * blockDim.x) {
+        const int s = i / Nfp, m = i - s * Nfp;
+        const int2 hp = pp.hpush[s];
+        double r[6];
+        load_rec(y + send_off[i], r);
+        store_rec(pp.peer_out[hp.x & 0xff] + ((size_t)hp.y * Nfp + m) * 6, r);
+    }
+    p2p_signal(pp);
 }
 
 // ---- layout conversion between the reference layout [6][Nloc] (Fields.h:45-65) and the aos device layout ---------------

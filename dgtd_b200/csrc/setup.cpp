@@ -259,10 +259,23 @@ HostOp build_host_op(const Mesh &m, const Options &o)
         return a.keyF < b.keyF;
     });
     H.n_halo_faces = (int)shared.size();
+    // every rank holds the whole mesh and the partitioning, so the peer's own enumeration is known without a message:
+    // shared[r][q] = faces rank r shares with rank q; a peer lists its blocks by ascending peer rank (as above)
+    std::map<std::pair<int, int>, int> sharedCnt;
+    if (o.nranks > 1)
+        for (int e = 0; e < NE; e++)
+            for (int f = 0; f < nf; f++) {
+                const int e2 = nbrE[(size_t)e * nf + f];
+                if (e2 >= 0 && part[e2] != part[e]) sharedCnt[{part[e], part[e2]}]++;
+            }
+    auto remote_block = [&](int peer, int &off, int &idx) {   // where MY block starts in the peer's halo slots / peer list
+        off = idx = 0;
+        for (auto it = sharedCnt.lower_bound({peer, 0}); it != sharedCnt.end() && it->first.first == peer && it->first.second < o.rank; ++it) { off += it->second; idx++; }
+    };
     std::map<std::pair<int, int>, int> haloSlot;   // (le, f) -> slot
     for (size_t s = 0; s < shared.size(); s++) {
         const Shared &sh = shared[s];
-        if (H.peers.empty() || H.peers.back().rank != sh.peer) { PeerPlan pp; pp.rank = sh.peer; pp.send_off = pp.recv_off = (int)s; H.peers.push_back(pp); }
+        if (H.peers.empty() || H.peers.back().rank != sh.peer) { PeerPlan pp; pp.rank = sh.peer; pp.send_off = pp.recv_off = (int)s; remote_block(sh.peer, pp.remote_off, pp.remote_idx); H.peers.push_back(pp); }
         H.peers.back().nfaces++;
         haloSlot[{sh.le, sh.f}] = (int)s;
         // what I send for this face: my nodes in the RECEIVER's face-node order

@@ -8,6 +8,7 @@
 #include "../../include/dgtd_b200.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 
 namespace dgtd {
@@ -68,6 +69,7 @@ WgPlan build_wg_plan(const HostOp &H)
     };
 
     // ---- face descriptors ---------------------------------------------------------------------------------------------------
+    const bool dbg_nonbr = std::getenv("DGTD_B200_DBG_NONBR") != nullptr;   // timing experiment only (wrong results)
     W.desc.assign((size_t)W.NEpad * 8, 0);
     for (int e = 0; e < W.NEpad; e++)
         for (int f = 0; f < 4; f++) {
@@ -80,6 +82,7 @@ WgPlan build_wg_plan(const HostOp &H)
             if (row > FI_TAB_MASK) throw Error(DGTD_ERR_UNSUPPORTED, "too many distinct face orientations");
             code = (code & ~(FI_TAB_MASK << FI_TAB_SHIFT)) | (row << FI_TAB_SHIFT);
             fo[0] = nb; fo[1] = code;
+            if (dbg_nonbr && nb >= 0 && (nb >> 3) != (e >> 3)) { fo[0] = -1; fo[1] = 0; }   // experiment: no trace leaves the group
         }
 
     // ---- DMMA B fragments (m8n8k4: lane l holds B[k = l&3][n = l>>2]) ------------------------------------------------------
@@ -114,6 +117,22 @@ WgPlan build_wg_plan(const HostOp &H)
             if (out < Np && !(q & 1)) W.bfrag[lbase + ((size_t)s * NT + NT - 1) * 32 + l] = L(out);
         }
 
+    // ---- direct halo push: what the face behind halo slot s sends, in the receiver's face-node order, and where ------------
+    W.hpush.assign((size_t)H.n_halo_faces * 2, 0);
+    {
+        std::map<std::vector<uint8_t>, int> pushRow;
+        for (size_t pi = 0; pi < H.peers.size(); pi++) {
+            const PeerPlan &pp = H.peers[pi];
+            for (int s = pp.send_off; s < pp.send_off + pp.nfaces; s++) {
+                std::vector<uint8_t> row(16, 0);
+                for (int m = 0; m < Nfp; m++) row[m] = (uint8_t)W.ref2dev[H.send_node[(size_t)s * Nfp + m] % Np];
+                auto it = pushRow.find(row);
+                const int id = it != pushRow.end() ? it->second : (pushRow[row] = put_row(row));
+                W.hpush[(size_t)s * 2] = (int)pi | (id << 8);
+                W.hpush[(size_t)s * 2 + 1] = pp.remote_off + (s - pp.send_off);
+            }
+        }
+    }
     // ---- halo pack list ---------------------------------------------------------------------------------------------------
     W.send_off.resize(H.send_node.size());
     for (size_t s = 0; s < H.send_node.size(); s++)

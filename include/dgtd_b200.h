@@ -140,15 +140,25 @@ long long dgtd_launch_count(const dgtd_ctx *);
 /* which stage kernel this context runs (name, tiling, launch shape) — for benchmark reports                */
 int  dgtd_kernel_info(const dgtd_ctx *, char *buf, int cap);
 
-/* ---- multi-GPU halo exchange (one context per rank/GPU, NCCL over NVLink) ----------------------- */
+/* ---- multi-GPU halo exchange (one context per rank/GPU over NVLink) ------------------------------
+ * Replaces the six blocking MPI neighbour exchanges of GlobalEvolution::Mult (GlobalEvolution.cpp:763-774).
+ * dgtd_comm_init is collective: NCCL bootstrap, then (tetrahedra, order <= 4) every rank maps its neighbours' halo
+ * buffers with CUDA IPC; from then on the stage kernel itself stores the traces of its partition faces into the
+ * neighbour's buffer and only the warps owning such a face wait for the neighbour's epoch flag (no pack kernel, no
+ * collective on the path).  If IPC is unavailable on any rank, all ranks use ncclSend/ncclRecv instead.
+ * dgtd_destroy of a multi-rank context is collective too (neighbours must stop storing before a buffer is freed).   */
 int  dgtd_comm_unique_id(void *id128);                    /* rank 0: ncclGetUniqueId              */
-int  dgtd_comm_init(dgtd_ctx *, const void *id128);       /* all ranks: ncclCommInitRank          */
+int  dgtd_comm_init(dgtd_ctx *, const void *id128);       /* all ranks                            */
+#define DGTD_HALO_NONE 0   /* single rank                                         */
+#define DGTD_HALO_NCCL 1   /* pack kernel + ncclSend/ncclRecv per RHS evaluation  */
+#define DGTD_HALO_P2P  2   /* peer-memory stores fused into the stage kernel      */
+int  dgtd_halo_mode(const dgtd_ctx *);
 /* bytes this rank sends per RHS evaluation (6 * Nfp * shared faces * 8)                          */
 int  dgtd_halo_bytes(const dgtd_ctx *, long long *bytes);
 
 /* Host-only diagnostic (no CUDA, no compute): copies one of the flat tables a rank would upload — "dims", "D", "lift",
- * "nodes", "fnodes", "geo", "finfo", "ftab", "elem_gid", "tfsf_xyz", "gate_xyz", "tfsf_side", "send_node", "peers",
- * "node_coords", and for tetrahedra the plan of the tensor-core kernel "blk_dims", "blk_geo", "blk_desc", "blk_afrag",
+ * "nodes", "fnodes", "geo", "finfo", "ftab", "elem_gid", "tfsf_xyz", "gate_xyz", "tfsf_side", "send_node", "peers", "peers5",
+ * "node_coords", the plan of the warp-per-group kernel "wg_hpush", "wg_tab", "wg_desc", "wg_send_off", "wg_dev2ref", and for tetrahedra the plan of the tensor-core kernel "blk_dims", "blk_geo", "blk_desc", "blk_afrag",
  * "blk_send_off" — so that tests can check the setup against the oracle without a GPU.                            */
 int  dgtd_setup_query(const dgtd_mesh *, const dgtd_options *, const char *name, void *buf, long long cap_bytes, long long *size_bytes);
 

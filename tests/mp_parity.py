@@ -57,10 +57,23 @@ def main():
         dist.all_reduce(cnt)
         assert int(cnt.min()) == 1 and int(cnt.max()) == 1, "partition does not tile the mesh"
         assert ev.halo_bytes() > 0, "no halo faces: the case does not exercise the exchange"
+        want_mode = os.environ.get("DGTD_EXPECT_HALO_MODE")
+        if want_mode is not None and "stage_wg_kernel" in ev.kernel_info():
+            assert ev.halo_mode() == int(want_mode), f"halo mode {ev.halo_mode()}, expected {want_mode}: {ev.kernel_info()}"
+        # a second pass on the same context: Mult between runs invalidates the pushed traces, the run must re-send them
+        ev.set_state(dat["x0_f64"])
+        ev.Step(meta["t0"], meta["dt"])
+        ev.SetTime(meta["t0"])
+        k2 = ev.Mult(dat["x0_f64"])
+        ev.set_state(dat["x0_f64"])
+        ev.run(meta["t0"], meta["dt"], meta["steps"])
+        x2 = ev.get_state(np.zeros(6 * N))
+        e_mult = max(e_mult, rel_l2(k2[mask], dat["k0_f64"][mask]))
+        e_run = max(e_run, rel_l2(x2[mask], dat["x_final_f64"][mask]))
         err = torch.tensor([e_mult, e_run], dtype=torch.float64, device="cuda")
         dist.all_reduce(err, op=dist.ReduceOp.MAX)
         if rank == 0:
-            print(f"mp_parity {name}: world {world}, Mult rel-L2 {err[0].item():.2e}, run rel-L2 {err[1].item():.2e}, halo bytes/rhs {ev.halo_bytes()}")
+            print(f"mp_parity {name}: world {world}, Mult rel-L2 {err[0].item():.2e}, run rel-L2 {err[1].item():.2e}, halo bytes/rhs {ev.halo_bytes()}, halo mode {ev.halo_mode()}")
         worst = max(worst, float(err.max().item()))
         ev.close()
     dist.destroy_process_group()

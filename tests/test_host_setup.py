@@ -162,6 +162,45 @@ def test_partitioner_and_halo_plan_two_ranks_in_process():
                     assert np.abs(mine - theirs).max() < 1e-14
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_direct_push_plan_is_consistent_across_ranks(world):
+    """Peer-memory halo path (kernels_wg.cuh: WgP2P): the slot a rank stores a face's traces into on its neighbour must be
+    the slot the neighbour reads for that face, in the neighbour's face-node order; flag slots must be mutually consistent."""
+    pb, _ = load_golden("box3d_p3_pec_upwind")
+    O = HesthavenOracle(pb)
+    mesh, kw = product_mesh_and_kwargs(pb)
+    Np, Nfp = O.Np, O.Nfp
+    xyz = O.xyz.reshape(-1, 3)
+    R = {}
+    for r in range(world):
+        q = lambda name, dt: _q(mesh, kw, name, dt, rank=r, nranks=world)
+        R[r] = dict(gid=q("elem_gid", np.int32), peers=q("peers5", np.int32).reshape(-1, 5), hpush=q("wg_hpush", np.int32).reshape(-1, 2),
+                    tab=q("wg_tab", np.uint8).reshape(-1, 16), desc=q("wg_desc", np.int32).reshape(-1, 4, 2), d2r=q("wg_dev2ref", np.int32))
+    for r in range(world):
+        me = R[r]
+        # flag slots: my remote_idx at peer p is my position in p's peer list
+        for pi, (prank, nfaces, soff, roff, ridx) in enumerate(me["peers"]):
+            theirs = R[int(prank)]["peers"]
+            assert theirs[ridx, 0] == r and theirs[ridx, 1] == nfaces and theirs[ridx, 2] == roff
+        # halo slot -> (local element, face) on every rank
+        slot_face = {}
+        for le in range(len(me["gid"])):
+            for f in range(4):
+                nb = me["desc"][le, f, 0]
+                if nb <= -2:
+                    slot_face[-2 - nb] = (le, f)
+        assert len(slot_face) == len(me["hpush"]) > 0
+        for s, (le, f) in slot_face.items():
+            pi, row = me["hpush"][s, 0] & 0xff, me["hpush"][s, 0] >> 8
+            dst_rank, dst_slot = int(me["peers"][pi, 0]), int(me["hpush"][s, 1])
+            there = R[dst_rank]
+            # the receiving side: the face behind dst_slot, its canonical face nodes m = 0..Nfp-1
+            rle, rf = next((a, b) for a in range(len(there["gid"])) for b in range(4) if there["desc"][a, b, 0] == -2 - dst_slot)
+            want = xyz[there["gid"][rle] * Np + O.ref.fnodes[rf]]
+            have = xyz[me["gid"][le] * Np + me["d2r"][me["tab"][row, :Nfp]]]
+            assert np.abs(want - have).max() < 1e-14
+
+
 def test_halo_plan_world_size_2_gloo():
     """The same through two processes that exchange their send lists' coordinates over gloo (host logic of the N>1 path)."""
     script = os.path.join(ROOT, "tests", "mp_halo_plan_cpu.py")
