@@ -249,17 +249,16 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
             double jm[9];
 #pragma unroll
             for (int i = 0; i < 9; i++) jm[i] = ge[i];
-            const double idet = ge[22], nidet = -idet;
 #pragma unroll
             for (int ks = 0; ks < KSV; ks++) {
                 const int node = 4 * ks + j;
                 double u[6] = {0, 0, 0, 0, 0, 0};
                 if (4 * ks + 3 < Np || node < Np) load_rec(yrec + node * 6, u);
-                double ut[6];     // [0..2] u~E, [3..5] u~H
+                double ut[6];     // [0..2] u~E = -(J/det)^T E, [3..5] u~H = (J/det)^T H   (jm = J / det J, WgPlan::geo)
 #pragma unroll
                 for (int a = 0; a < 3; a++) {
-                    ut[a] = fma(jm[a], u[0], fma(jm[3 + a], u[1], jm[6 + a] * u[2])) * nidet;
-                    ut[3 + a] = fma(jm[a], u[3], fma(jm[3 + a], u[4], jm[6 + a] * u[5])) * idet;
+                    ut[a] = -fma(jm[a], u[0], fma(jm[3 + a], u[1], jm[6 + a] * u[2]));
+                    ut[3 + a] = fma(jm[a], u[3], fma(jm[3 + a], u[4], jm[6 + a] * u[5]));
                 }
                 const double *fr = sFragV + (ks * VT) * 32 + lane;
 #pragma unroll
@@ -287,6 +286,8 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
         // ---------------- face flux of (element e, face j) -> LIFT --------------------------------------------------------
         {
             const int tf = (code >> FI_TFSF_SHIFT) & FI_TFSF_MASK;
+            // dU = u+ - u- + c u-  =  u+ - (1 - c) u-   (boundary faces read u+ = u-; 1 - c is 1, 2 or 3: exact)
+            const double se1 = 1.0 - ce, sh1 = 1.0 - ch;
             double ji[9];
 #pragma unroll
             for (int i = 0; i < 9; i++) ji[i] = ge[9 + i];
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
                     else load_rec(nbase + tab_byte(nrow, s + PF) * 6, uQ[(s + PF) % (PF + 1)]);
                 }
 #pragma unroll
-                for (int c = 0; c < 3; c++) { dU[c] = fma(ce, uM[c], uP[c] - uM[c]); dU[3 + c] = fma(ch, uM[3 + c], uP[3 + c] - uM[3 + c]); }
+                for (int c = 0; c < 3; c++) { dU[c] = fma(-se1, uM[c], uP[c]); dU[3 + c] = fma(-sh1, uM[3 + c], uP[3 + c]); }   // u+ - u- (+ c u-)
                 if (TF && tf && inject) {
                     double inc[6];
                     const int m = tab_byte(sTab[4 + j], s);
@@ -378,7 +379,8 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
         double jm[9];
 #pragma unroll
         for (int i = 0; i < 9; i++) jm[i] = ge[i];
-        const double ie = ge[23], im = ge[24], se = ge[25];
+        const double de = ge[23], dm = ge[24], se = ge[25];          // det/eps, det/mu, sigma/eps  (jm = J / det)
+        const double ae = A.a * de, am = A.a * dm, be = A.b * de, bm = A.b * dm;
         const bool keep_y = A.has_sigma != 0;        // the conductivity term reads E of y_in in the epilogue
         const int gnext = g + gstride;
         if (!keep_y) {
@@ -404,18 +406,21 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
                         kr[c] = acc[f3 + (cc + 2) % 3][NT - 1][0] + acc[f3 + (cc + 1) % 3][NT - 1][1];
                     }
                 }
-                double k[6];
+                double k[6];     // (J/det) k~ : the material factor det/eps, det/mu joins the Runge-Kutta coefficient below
 #pragma unroll
                 for (int d = 0; d < 3; d++) {
-                    k[d] = fma(jm[3 * d], kr[0], fma(jm[3 * d + 1], kr[1], jm[3 * d + 2] * kr[2])) * ie;
-                    k[3 + d] = fma(jm[3 * d], kr[3], fma(jm[3 * d + 1], kr[4], jm[3 * d + 2] * kr[5])) * im;
+                    k[d] = fma(jm[3 * d], kr[0], fma(jm[3 * d + 1], kr[1], jm[3 * d + 2] * kr[2]));
+                    k[3 + d] = fma(jm[3 * d], kr[3], fma(jm[3 * d + 1], kr[4], jm[3 * d + 2] * kr[5]));
                 }
                 const int off = (e * Np + node) * 6;
-                if (keep_y) {
-                    double uo[6];
-                    load_rec(wY + off, uo);
+                double ca[6] = {ae, ae, ae, am, am, am}, cb[6] = {be, be, be, bm, bm, bm};
+                if (keep_y || MODE == MODE_MULT) {       // the plain k is needed: conductivity term, or Mult's output
+                    double uo[6] = {0, 0, 0, 0, 0, 0};
+                    if (keep_y) load_rec(wY + off, uo);
 #pragma unroll
-                    for (int d = 0; d < 3; d++) k[d] -= se * uo[d];
+                    for (int d = 0; d < 3; d++) { k[d] = fma(de, k[d], -(se * uo[d])); k[3 + d] *= dm; }
+#pragma unroll
+                    for (int c = 0; c < 6; c++) { ca[c] = A.a; cb[c] = A.b; }
                 }
                 double xv[6], zv[6], o[6], zn[6];
                 if (LOAD_X) load_rec(wX + off, xv);
@@ -423,9 +428,9 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
 #pragma unroll
                 for (int c = 0; c < 6; c++) {
                     if (MODE == MODE_MULT) o[c] = k[c];
-                    else if (MODE == MODE_STAGE1) { o[c] = fma(A.a, k[c], xv[c]); zn[c] = fma(A.b, k[c], xv[c]); }
-                    else if (MODE == MODE_STAGE23) { o[c] = fma(A.a, k[c], xv[c]); zn[c] = fma(A.b, k[c], zv[c]); }
-                    else zn[c] = fma(A.b, k[c], zv[c]);            // stage 4: new x, formed in the z buffer
+                    else if (MODE == MODE_STAGE1) { o[c] = fma(ca[c], k[c], xv[c]); zn[c] = fma(cb[c], k[c], xv[c]); }
+                    else if (MODE == MODE_STAGE23) { o[c] = fma(ca[c], k[c], xv[c]); zn[c] = fma(cb[c], k[c], zv[c]); }
+                    else zn[c] = fma(cb[c], k[c], zv[c]);          // stage 4: new x, formed in the z buffer
                 }
                 if (STORE_X) store_rec(wX + off, o);
                 if (STORE_Z) store_rec(wZ + off, zn);

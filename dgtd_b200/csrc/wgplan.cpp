@@ -36,9 +36,10 @@ WgPlan build_wg_plan(const HostOp &H)
         double *g = &W.geo[(size_t)e * BLK_GEO];
         if (e < NE) {
             const double *v1 = &H.geo[(size_t)e * GEO_STRIDE], *jc = &H.jac[(size_t)e * 10];
-            for (int i = 0; i < 9; i++) { g[i] = jc[i]; g[9 + i] = v1[i]; }
+            // J / det J (covariant transform and push-forward share it), J^-1, fscale, 1/det, det/eps, det/mu, sigma/eps
+            for (int i = 0; i < 9; i++) { g[i] = jc[i] / jc[9]; g[9 + i] = v1[i]; }
             for (int f = 0; f < 4; f++) g[18 + f] = v1[9 + f];
-            g[22] = 1.0 / jc[9]; g[23] = v1[13]; g[24] = v1[14]; g[25] = v1[15];
+            g[22] = 1.0 / jc[9]; g[23] = jc[9] * v1[13]; g[24] = jc[9] * v1[14]; g[25] = v1[15];
         } else {   // padding element: unit geometry, vacuum; its state stays zero
             g[0] = g[4] = g[8] = 1.0; g[9] = g[13] = g[17] = 1.0;
             g[18] = g[19] = g[20] = g[21] = 1.0; g[22] = g[23] = g[24] = 1.0;
