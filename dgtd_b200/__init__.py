@@ -5,8 +5,8 @@ include/dgtd_b200.h) plus the header-only C++ shells in dgtd_b200/mfem_shell/B20
 ctypes binding used by tests/ and bench.py; it contains no numerics and NO CPU fallback — loading
 fails loudly if the shared library has not been built (see __graft_entry__.build()).
 """
-from .api import (BC_NONE, BC_PEC, BC_PMC, BC_SMA, DgtdError, Evolution, Mesh, PlaneWave, lib, lib_path,
+from .api import (BC_NONE, BC_PEC, BC_PMC, BC_SMA, DgtdError, Evolution, Gather, Mesh, PlaneWave, lib, lib_path,
                   setup_query, HEADER_SYMBOLS)
 
-__all__ = ["BC_NONE", "BC_PEC", "BC_PMC", "BC_SMA", "DgtdError", "Evolution", "Mesh", "PlaneWave", "lib",
+__all__ = ["BC_NONE", "BC_PEC", "BC_PMC", "BC_SMA", "DgtdError", "Evolution", "Gather", "Mesh", "PlaneWave", "lib",
            "lib_path", "setup_query", "HEADER_SYMBOLS"]

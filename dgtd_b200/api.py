@@ -60,6 +60,12 @@ def _load():
     L.dgtd_launch_count.argtypes = [C.c_void_p]
     L.dgtd_kernel_info.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.dgtd_halo_mode.argtypes = [C.c_void_p]
+    L.dgtd_gather_destroy.restype = None
+    L.dgtd_gather_destroy.argtypes = [C.c_void_p]
+    L.dgtd_gather_create.argtypes = [C.c_void_p, C.c_longlong, C.POINTER(C.c_longlong), C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]
+    L.dgtd_gather_dofs.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+    L.dgtd_gather_launch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+    L.dgtd_gather_wait.argtypes = [C.c_void_p, C.c_void_p]
     L.dgtd_mesh_destroy.restype = None
     L.dgtd_mesh_destroy.argtypes = [C.c_void_p]
     L.dgtd_destroy.restype = None
@@ -130,6 +136,15 @@ class Mesh:
         _ck(lib.dgtd_mesh_get_arrays(self._h, _dp(v), _ip(e), _ip(ea), _ip(b), _ip(ba)))
         return v, e, ea, b, ba
 
+    def boundary_elements(self, attrs):
+        """(element, local face) pairs on boundary elements tagged with `attrs` (both sides of interior surfaces)."""
+        a = np.ascontiguousarray(list(attrs), np.int32)
+        n = C.c_longlong()
+        _ck(lib.dgtd_mesh_boundary_elements(self._h, len(a), _ip(a), C.c_longlong(0), None, C.byref(n)))
+        pairs = np.zeros((n.value, 2), np.int32)
+        _ck(lib.dgtd_mesh_boundary_elements(self._h, len(a), _ip(a), C.c_longlong(n.value), _ip(pairs), C.byref(n)))
+        return pairs
+
     def partition(self, nranks):
         p = np.zeros(self.ne, np.int32)
         _ck(lib.dgtd_mesh_partition(self._h, nranks, _ip(p)))
@@ -174,6 +189,37 @@ def setup_query(mesh: Mesh, name: str, dtype, *, order, alpha=1.0, bdr=None, tfs
     buf = np.zeros(n.value // np.dtype(dtype).itemsize, dtype)
     _ck(lib.dgtd_setup_query(mesh._h, C.byref(o), name.encode(), buf.ctypes.data_as(C.c_void_p), C.c_longlong(buf.nbytes), C.byref(n)))
     return buf
+
+
+class Gather:
+    """Asynchronous snapshot of a fixed dof list (probes, RCS surface export): launch() queues a gather kernel on the compute
+    stream and a device-to-host copy on a side stream, wait() makes `out` readable.  dgtd_gather_* in the C ABI."""
+
+    def __init__(self, ev, dofs):
+        dofs = np.ascontiguousarray(dofs, np.int64)
+        self._ev, self._h = ev, C.c_void_p()
+        n = C.c_longlong()
+        _ck(lib.dgtd_gather_create(ev._h, C.c_longlong(len(dofs)), dofs.ctypes.data_as(C.POINTER(C.c_longlong)), C.byref(self._h), C.byref(n)))
+        self.n_local = n.value
+        self.dofs = np.zeros(self.n_local, np.int64)
+        if self.n_local:
+            _ck(lib.dgtd_gather_dofs(self._h, self.dofs.ctypes.data_as(C.POINTER(C.c_longlong))))
+
+    def launch(self, out):
+        """out: float64 array [6, n_local] (pinned memory makes the copy asynchronous); not readable before wait()."""
+        assert out.dtype == np.float64 and out.size == 6 * self.n_local and out.flags["C_CONTIGUOUS"]
+        _ck(lib.dgtd_gather_launch(self._ev._h, self._h, _dp(out)))
+
+    def wait(self):
+        _ck(lib.dgtd_gather_wait(self._ev._h, self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.dgtd_gather_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
 
 
 class Evolution:

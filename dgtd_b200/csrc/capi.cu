@@ -822,6 +822,104 @@ int dgtd_sample(dgtd_ctx *c, int npts, const int *elem, const double *shape, dou
     CU(cudaStreamSynchronize(c->stream));
     GUARD_END
 }
+struct dgtd_gather {
+    dgtd_ctx *c = nullptr;
+    std::vector<long long> dofs;          // owned dofs, global numbering, output order
+    DevBuf<long long> off;                // offset of component 0 in the device state
+    long long cstride = 1;
+    DevBuf<double> stage;                 // [6][n]
+    cudaStream_t side = nullptr;
+    cudaEvent_t ready = nullptr, done = nullptr;
+    bool pending = false;
+    ~dgtd_gather()
+    {
+        if (done) { if (pending) cudaEventSynchronize(done); cudaEventDestroy(done); }
+        if (ready) cudaEventDestroy(ready);
+        if (side) cudaStreamDestroy(side);
+    }
+};
+
+int dgtd_gather_create(dgtd_ctx *c, long long n, const long long *dofs, dgtd_gather **out, long long *n_local)
+{
+    GUARD_BEGIN
+    if (!c || !out || n < 0 || (n && !dofs)) throw Error(DGTD_ERR_ARG, "dgtd_gather_create: bad argument");
+    CU(cudaSetDevice(c->device));
+    const int Np = c->H.Np;
+    std::vector<int> g2l((size_t)c->H.NEglob, -1);
+    for (int le = 0; le < c->H.NEloc; le++) g2l[(size_t)c->H.elem_gid[le]] = le;
+    auto g = std::make_unique<dgtd_gather>();
+    g->c = c;
+    std::vector<long long> off;
+    for (long long i = 0; i < n; i++) {
+        const long long d = dofs[i];
+        if (d < 0 || d >= c->Nglob) throw Error(DGTD_ERR_ARG, "dgtd_gather_create: dof out of range");
+        const int le = g2l[(size_t)(d / Np)], node = (int)(d % Np);
+        if (le < 0) continue;   // another rank's
+        g->dofs.push_back(d);
+        if (c->wg) off.push_back(((long long)le * Np + c->WP.ref2dev[node]) * 6);
+        else if (c->blocked) off.push_back(blocked_offset(Np, le, node));
+        else off.push_back((long long)le * Np + node);
+    }
+    g->cstride = c->blocked ? 1 : c->Nloc;
+    g->off.upload(off, 1);
+    g->stage.alloc(std::max<size_t>(1, 6 * off.size()));
+    CU(cudaStreamCreateWithFlags(&g->side, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&g->ready, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&g->done, cudaEventDisableTiming));
+    if (n_local) *n_local = (long long)g->dofs.size();
+    *out = g.release();
+    GUARD_END
+}
+int dgtd_gather_dofs(const dgtd_gather *g, long long *dofs_local)
+{
+    if (!g || !dofs_local) return fail(DGTD_ERR_ARG, "null argument");
+    std::memcpy(dofs_local, g->dofs.data(), g->dofs.size() * sizeof(long long));
+    return DGTD_OK;
+}
+int dgtd_gather_launch(dgtd_ctx *c, dgtd_gather *g, double *host_out)
+{
+    GUARD_BEGIN
+    if (!c || !g || g->c != c || !host_out) throw Error(DGTD_ERR_ARG, "dgtd_gather_launch: bad argument");
+    CU(cudaSetDevice(c->device));
+    const long long n = (long long)g->dofs.size();
+    if (n == 0) return DGTD_OK;
+    if (g->pending) CU(cudaStreamWaitEvent(c->stream, g->done, 0));          // the previous snapshot must have left the staging buffer
+    gather_kernel<<<(int)std::min<long long>(592, (n + 255) / 256), 256, 0, c->stream>>>(c->x.p, g->off.p, g->cstride, n, g->stage.p);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(g->ready, c->stream));
+    CU(cudaStreamWaitEvent(g->side, g->ready, 0));
+    CU(cudaMemcpyAsync(host_out, g->stage.p, sizeof(double) * 6 * (size_t)n, cudaMemcpyDeviceToHost, g->side));
+    CU(cudaEventRecord(g->done, g->side));
+    g->pending = true;
+    GUARD_END
+}
+int dgtd_gather_wait(dgtd_ctx *c, dgtd_gather *g)
+{
+    GUARD_BEGIN
+    if (!c || !g || g->c != c) throw Error(DGTD_ERR_ARG, "dgtd_gather_wait: bad argument");
+    if (g->pending) { CU(cudaEventSynchronize(g->done)); g->pending = false; }
+    GUARD_END
+}
+void dgtd_gather_destroy(dgtd_gather *g)
+{
+    if (!g) return;
+    if (g->c) cudaSetDevice(g->c->device);
+    delete g;
+}
+int dgtd_mesh_boundary_elements(const dgtd_mesh *m, int n_attr, const int *bdr_attr, long long cap_pairs, int *pairs, long long *n_pairs)
+{
+    GUARD_BEGIN
+    if (!m || !n_pairs || n_attr < 0 || (n_attr && !bdr_attr)) throw Error(DGTD_ERR_ARG, "dgtd_mesh_boundary_elements: bad argument");
+    std::vector<int> attrs(bdr_attr, bdr_attr + n_attr);
+    std::vector<int> pr = boundary_element_faces(m->m, attrs);
+    *n_pairs = (long long)pr.size() / 2;
+    if (pairs) {
+        if ((long long)pr.size() / 2 > cap_pairs) throw Error(DGTD_ERR_ARG, "buffer too small");
+        std::memcpy(pairs, pr.data(), pr.size() * sizeof(int));
+    }
+    GUARD_END
+}
 int dgtd_synchronize(dgtd_ctx *c)
 {
     GUARD_BEGIN

@@ -106,6 +106,7 @@ struct HostOp {
     bool tfsf_gate = true;
 };
 HostOp build_host_op(const Mesh &m, const Options &o);
+std::vector<int> boundary_element_faces(const Mesh &m, const std::vector<int> &attrs);
 
 // ---- "blocked" plan of the DMMA stage kernel (3-D only) ----------------------------------------------------------------
 // Device state layout: groups of 8 consecutive local elements; group g holds Np*8*6 doubles indexed [node j][e8][comp c]

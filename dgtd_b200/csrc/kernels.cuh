@@ -293,6 +293,16 @@ __global__ void sumsq_kernel(const double *x, long long n, double *out)
 }
 
 // halo pack: send[c][s] = y[c][send_node[s]]
+// Probe / surface-export gather: out[c][i] = component c of the scalar dof whose component-0 value sits at off[i]
+// (component stride cstride: 1 in the record layouts, Nloc in the reference layout).
+__global__ void gather_kernel(const double *x, const long long *off, long long cstride, long long n, double *out)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double *p = x + off[i];
+#pragma unroll
+        for (int c = 0; c < 6; c++) out[c * n + i] = p[c * cstride];
+    }
+}
 __global__ void pack_kernel(const double *y, long long stride, const int *send_node, int ns, double *send, long long sstride)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {

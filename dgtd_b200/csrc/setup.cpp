@@ -103,6 +103,34 @@ void node_coords(const Mesh &m, const RefElem &ref, std::vector<double> &xyz)
     }
 }
 
+// (element, local face) pairs lying on boundary elements with one of the given attributes; for interior surfaces both
+// sides are listed, lower element id first.  Selection step of NearToFarFieldSubMesher (SubMesher.cpp:832-905).
+std::vector<int> boundary_element_faces(const Mesh &m, const std::vector<int> &attrs)
+{
+    const int dim = m.dim, nf = dim + 1, NE = m.ne();
+    std::set<int> want(attrs.begin(), attrs.end());
+    std::vector<FaceKey> sorted((size_t)NE * nf);
+    for (int e = 0; e < NE; e++) for (int f = 0; f < nf; f++) {
+        FaceKey &k = sorted[(size_t)e * nf + f];
+        k.v[0] = k.v[1] = k.v[2] = -1; int c = 0;
+        for (int q = 0; q < nf; q++) if (q != f) k.v[c++] = m.elems[(size_t)e * nf + q];
+        std::sort(k.v, k.v + dim);
+        k.e = e; k.f = f;
+    }
+    std::sort(sorted.begin(), sorted.end(), [](const FaceKey &a, const FaceKey &b) { return a < b || (!(b < a) && a.e < b.e); });
+    std::vector<int> out;
+    for (int b = 0; b < m.nbe(); b++) {
+        if (!want.count(m.bdr_attr[b])) continue;
+        FaceKey k; k.v[0] = k.v[1] = k.v[2] = -1; k.e = k.f = 0;
+        for (int c = 0; c < dim; c++) k.v[c] = m.bdr[(size_t)b * dim + c];
+        std::sort(k.v, k.v + dim);
+        auto it = std::lower_bound(sorted.begin(), sorted.end(), k);
+        if (it == sorted.end() || !it->same(k)) throw Error(DGTD_ERR_MESH, "boundary element " + std::to_string(b) + " is not a face of any element");
+        for (; it != sorted.end() && it->same(k); ++it) { out.push_back(it->e); out.push_back(it->f); }
+    }
+    return out;
+}
+
 HostOp build_host_op(const Mesh &m, const Options &o)
 {
     HostOp H;

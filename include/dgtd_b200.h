@@ -134,6 +134,25 @@ int  dgtd_rk4_run(dgtd_ctx *, double t0, double dt, int nsteps);
 int  dgtd_norm2_local(dgtd_ctx *, double *sumsq);
 /* point probes: field values at npts (local element, Np shape weights) -> out[npts][6]            */
 int  dgtd_sample(dgtd_ctx *, int npts, const int *local_elem, const double *shape, double *out6);
+/* ---- probes, field / RCS-surface export: periodic asynchronous device-to-host copies ------------------------------
+ * A gather is a fixed list of scalar dofs in the reference numbering (element * Np + node, Fields.h:45-65).  Every launch
+ * snapshots the six field values of the locally owned ones, in list order, into host_out[6][n_local] WITHOUT stopping
+ * the time loop: gather kernel on the compute stream, device-to-host copy on a side stream (pin host_out for a truly
+ * asynchronous copy), dgtd_gather_wait before reading.  Steps issued after the launch do not alter the snapshot.
+ * Replaces RCSSurfaceExporter::transferFields (RCSSurfaceExporter.cpp:71-79: six TransferMaps + host write per export
+ * step), the FieldProbe / PointProbe reads of ProbesManager (Solver.cpp:550) and the per-step full-state D2H they imply. */
+typedef struct dgtd_gather dgtd_gather;
+int  dgtd_gather_create(dgtd_ctx *, long long n, const long long *dofs, dgtd_gather **out, long long *n_local);
+/* the owned dofs of the gather (global numbering), in output order: dofs_local[n_local]           */
+int  dgtd_gather_dofs(const dgtd_gather *, long long *dofs_local);
+int  dgtd_gather_launch(dgtd_ctx *, dgtd_gather *, double *host_out);
+int  dgtd_gather_wait(dgtd_ctx *, dgtd_gather *);
+void dgtd_gather_destroy(dgtd_gather *);
+/* Host-only helper for surface exports: the (global element, local face) pairs lying on boundary elements with one of
+ * the given attributes — NearToFarFieldSubMesher's selection (SubMesher.cpp:832-905) keeps one element per face; here
+ * both sides are listed, lower element id first (MFEM's Elem1), and the caller picks.  pairs[2*k] = element, [2*k+1] =
+ * face; returns the number of pairs through n_pairs (call with pairs = NULL to size the buffer).                    */
+int  dgtd_mesh_boundary_elements(const dgtd_mesh *, int n_attr, const int *bdr_attr, long long cap_pairs, int *pairs, long long *n_pairs);
 int  dgtd_synchronize(dgtd_ctx *);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches)               */
 long long dgtd_launch_count(const dgtd_ctx *);

@@ -208,3 +208,26 @@ def test_halo_plan_world_size_2_gloo():
            "--master-port", "29431", script]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, OMP_NUM_THREADS="1"))
     assert r.returncode == 0 and r.stdout.count("HALO_PLAN_OK") == 2, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_boundary_element_listing_for_surface_exports():
+    """dgtd_mesh_boundary_elements: every tagged boundary face is reported with the element(s) it belongs to
+    (selection step of NearToFarFieldSubMesher, SubMesher.cpp:832-905); interior surfaces list both sides."""
+    pb, _ = load_golden("tfsf3d_p2_on")
+    mesh, kw = product_mesh_and_kwargs(pb)
+    tags = list(pb.tfsf_tags)
+    pairs = mesh.boundary_elements(tags)
+    nb = int(np.isin(pb.bdr_attr, tags).sum())
+    assert nb > 0 and len(pairs) == 2 * nb           # TF/SF surface is interior: two sides per face
+    elems = np.asarray(pb.elems)
+    bdr = np.asarray(pb.bdr)[np.isin(pb.bdr_attr, tags)]
+    want = {tuple(sorted(f)) for f in bdr.tolist()}
+    got = {}
+    for e, f in pairs.tolist():
+        got.setdefault(tuple(sorted(np.delete(elems[e], f).tolist())), []).append(e)
+    assert set(got) == want
+    assert all(len(v) == 2 and v[0] < v[1] for v in got.values())
+    # true boundary: one side
+    ext = [a for a in set(np.asarray(pb.bdr_attr).tolist()) if a not in tags]
+    p2 = mesh.boundary_elements(ext)
+    assert len(p2) == int(np.isin(pb.bdr_attr, ext).sum())
