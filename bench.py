@@ -36,7 +36,7 @@ B_ALG = {1: 40.0 + 200.0 / (6 * 4), 2: 40.0 + 200.0 / (6 * 10), 3: 40.0 + 200.0 
 
 def workload_name(n_gpus, cubes):
     return (f"3D tet PEC box (Kuhn Cartesian {cubes * n_gpus}x{cubes}x{cubes} cubes x6 tets), order {ORDER}, upwind alpha=1, "
-            f"{cubes ** 3 * 6 * n_gpus} tets, {cubes ** 3 * 6 * n_gpus * 20 * 6} DOFs, RCB slabs, classical RK4")
+            f"{cubes ** 3 * 6 * n_gpus} tets, {cubes ** 3 * 6 * n_gpus * (ORDER + 1) * (ORDER + 2) * (ORDER + 3)} DOFs, RCB slabs, classical RK4")
 
 
 def peaks():
@@ -118,16 +118,19 @@ def cpu_reference(cubes, steps, warmup, threads=None):
 
 
 def main():
+    global ORDER
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cubes", type=int, default=CUBES_PER_GPU, help="cubes per axis per GPU (default 32)")
+    ap.add_argument("--order", type=int, default=ORDER, help="polynomial order (default 3 = the headline workload; others are side measurements)")
     ap.add_argument("--cpu-cubes", type=int, default=6, help="box size of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--e2e-steps", type=int, default=3)
     args = ap.parse_args()
+    ORDER = args.order
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -16,7 +16,7 @@ import numpy as np
 
 BC_NONE, BC_PEC, BC_PMC, BC_SMA = 0, 1, 2, 3
 _HERE = os.path.dirname(os.path.abspath(__file__))
-lib_path = os.path.join(_HERE, "libdgtd_b200.so")
+lib_path = os.environ.get("DGTD_B200_LIB") or os.path.join(_HERE, "libdgtd_b200.so")   # override: A/B builds of the same ABI
 _HEADER = os.path.join(os.path.dirname(_HERE), "include", "dgtd_b200.h")
 
 

@@ -105,7 +105,10 @@ struct WgArgs {
 template <int P> struct Wg {
     static constexpr int Np = (P + 1) * (P + 2) * (P + 3) / 6, Nfp = (P + 1) * (P + 2) / 2;
     static constexpr int NT = (Np + 7) / 8, KSV = (Np + 3) / 4, VT = (NT - 1) * 3 + 3;
-    static constexpr int NW = P <= 3 ? 8 : 4, T = 32 * NW;       // warps per CTA = groups in flight per SM
+#ifndef DGTD_WG_NW
+#define DGTD_WG_NW 8
+#endif
+    static constexpr int NW = P <= 3 ? DGTD_WG_NW : 4, T = 32 * NW;       // warps per CTA = groups in flight per SM
     static constexpr int GS = Np * BLK_E * 6;                    // doubles per group of one state vector
     static constexpr int NFV = KSV * VT, NFL = Nfp * NT, NFR = NFV + NFL;
     static constexpr int WGEO = BLK_E * BLK_GEO, WDESC = BLK_E * 4 * 2;   // doubles / ints per group

@@ -1,0 +1,319 @@
+// sm_100a warp-PAIR DMMA stage kernel (tetrahedra): the warp-per-group kernel of kernels_wg.cuh with each group of 8
+// elements carried by TWO warps that share the group's shared-memory buffers — warp role h = 0 forms the E rows of the
+// stage (k_E from u~_H and the E flux), h = 1 the H rows.
+//
+// Why (profiles/r1_wgv1_stage_ncu_summary.txt, tools: DGTD_WG_NW sweep): the one-warp kernel keeps 72 accumulator registers
+// and 25 KB of buffers per warp, so 8 warps fill an SM (2 per scheduler) and the FP64 pipe idles 28 % of the time on
+// latencies nobody covers (4 -> 8 warps per SM bought +35 %).  Halving the accumulator set per warp (36 registers at order
+// 3) lets 12 warps (3 per scheduler, 6 groups in flight) fit the register file at order 3, and 8 instead of 4 warps at
+// order 4, for ~12 % more FP64 ALU work (both warps form the jumps).
+//   * same state layout ("aos"), plan (WgPlan), operator fragments, TMA staging and peer-memory halo as kernels_wg.cuh;
+//   * role-dependent data is reached through pointer offsets (own = 3h, other = 3 - 3h doubles into a node record) and
+//     sign-folded operators, never through run-time register indexing;
+//   * the two warps of a pair meet at two named barriers per group: after the last read of y_in (the next group's y_in
+//     may land) and after the epilogue (the bulk stores and the halo push read complete records).
+// Reference semantics: src/evolution/HesthavenEvolution.cpp:450-542 with the `global` operator's coefficients
+// (src/components/DGOperatorFactory.h:469-573, 1268-1361), external/mfem-geg/linalg/ode.cpp:109-136.
+#pragma once
+#include "kernels_wg.cuh"
+
+namespace dgtd {
+
+#ifndef DGTD_WP_NG
+#define DGTD_WP_NG 6
+#endif
+template <int P> struct Wp {
+    static constexpr int Np = (P + 1) * (P + 2) * (P + 3) / 6, Nfp = (P + 1) * (P + 2) / 2;
+    static constexpr int NT = (Np + 7) / 8, KSV = (Np + 3) / 4, VT = (NT - 1) * 3 + 3;
+    static constexpr int NG = P <= 3 ? DGTD_WP_NG : 4, NW = 2 * NG, T = 32 * NW;   // groups in flight per SM, warps
+    static constexpr int GS = Np * BLK_E * 6;
+    static constexpr int NFV = KSV * VT, NFL = Nfp * NT, NFR = NFV + NFL;
+    static constexpr int WGEO = BLK_E * BLK_GEO, WDESC = BLK_E * 4 * 2;
+    static constexpr int WDBL = 3 * GS + WGEO + WDESC / 2;
+    static constexpr int TABROWS = 136;
+    static constexpr int oWarp = NFR * 32;
+    static constexpr size_t bTab = (size_t)(oWarp + NG * WDBL) * 8;
+    static constexpr size_t bBar = bTab + (size_t)TABROWS * 16;
+    static constexpr size_t smem_bytes = bBar + (size_t)NG * 2 * 8;
+    static_assert(Np - 8 * (NT - 1) <= 4, "mixed last tile");
+    static_assert((GS % 2) == 0 && (bTab % 16) == 0, "alignment");
+};
+
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void load3(const double *p, double *u) { u[0] = p[0]; u[1] = p[1]; u[2] = p[2]; }
+__device__ __forceinline__ void store3(double *p, const double *u) { p[0] = u[0]; p[1] = u[1]; p[2] = u[2]; }
+
+template <int P, int MODE, bool TF>
+__global__ void __launch_bounds__(Wp<P>::T, 1) stage_wp_kernel(const WgArgs A)
+{
+    using B = Wp<P>;
+    constexpr int Np = B::Np, Nfp = B::Nfp, NT = B::NT, KSV = B::KSV, VT = B::VT, GS = B::GS;
+    constexpr int NL = Np - 8 * (NT - 1);
+    constexpr int PF = 1;
+    constexpr bool LOAD_X = MODE == MODE_STAGE1 || MODE == MODE_STAGE23;
+    constexpr bool LOAD_Z = MODE == MODE_STAGE23 || MODE == MODE_STAGE4;
+    constexpr bool STORE_X = MODE != MODE_STAGE4, STORE_Z = MODE != MODE_MULT;
+    extern __shared__ __align__(128) unsigned char smem_wg[];
+    double *sm = reinterpret_cast<double *>(smem_wg);
+    const double *sFragV = sm, *sFragL = sm + B::NFV * 32;
+    const uint4 *sTab = reinterpret_cast<const uint4 *>(smem_wg + B::bTab);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, e = lane >> 2, j = lane & 3;
+    const int h = warp & 1, gs = warp >> 1;              // role (0: E rows, 1: H rows), group slot
+    const int own = 3 * h, oth = 3 - own;                // doubles into a node record: my output field / the other one
+    const bool leader = h == 0 && lane == 0;
+    double *wY = sm + B::oWarp + gs * B::WDBL, *wX = wY + GS, *wZ = wX + GS, *wGeo = wZ + GS;
+    const int2 *wDesc = reinterpret_cast<const int2 *>(wGeo + B::WGEO);
+    uint64_t *barY = reinterpret_cast<uint64_t *>(smem_wg + B::bBar) + 2 * gs, *barXZ = barY + 1;
+
+    for (int i = tid; i < B::NFR * 32; i += B::T) sm[i] = A.bfrag[i];
+    {
+        uint4 *dst = reinterpret_cast<uint4 *>(smem_wg + B::bTab);
+        const uint4 *src = reinterpret_cast<const uint4 *>(A.tab);
+        for (int i = tid; i < min(A.ntab, B::TABROWS); i += B::T) dst[i] = src[i];
+    }
+    if (leader) { mbar_init(barY, 1); mbar_init(barXZ, 1); }
+    if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem();
+    __syncthreads();
+
+    const int gstride = gridDim.x * B::NG;
+    int g = blockIdx.x * B::NG + gs;
+    bool halo_ready = A.pp.wait_epoch == 0;
+    const uint4 ownrow = sTab[j];
+    const bool inject = A.pw_on && (A.gate == nullptr || *A.gate >= 1e-16);
+    const double sgn = h ? -1.0 : 1.0;                   // u~_E = -(J/det)^T E feeds the H rows, u~_H = +(J/det)^T H the E rows
+
+    auto issue_y = [&](int gg) {
+        mbar_expect_tx(barY, (uint32_t)(GS * 8 + B::WGEO * 8 + B::WDESC * 4));
+        bulk_load(wY, A.yin + (size_t)gg * GS, GS * 8, barY);
+        bulk_load(wGeo, A.geo + (size_t)gg * B::WGEO, B::WGEO * 8, barY);
+        bulk_load(wGeo + B::WGEO, A.desc + (size_t)gg * B::WDESC, B::WDESC * 4, barY);
+    };
+    auto issue_xz = [&](int gg) {
+        mbar_expect_tx(barXZ, (uint32_t)(GS * 8) * ((LOAD_X ? 1 : 0) + (LOAD_Z ? 1 : 0)));
+        if (LOAD_X) bulk_load(wX, (MODE == MODE_STAGE1 ? A.yin : A.x) + (size_t)gg * GS, GS * 8, barXZ);
+        if (LOAD_Z) bulk_load(wZ, A.z + (size_t)gg * GS, GS * 8, barXZ);
+    };
+    if (leader && g < A.ngroups) { issue_y(g); if (LOAD_X || LOAD_Z) issue_xz(g); }
+
+    for (int it = 0; g < A.ngroups; g += gstride, it++) {
+        const uint32_t par = it & 1;
+        const double *ge = wGeo + e * BLK_GEO;
+        const double *yrec = wY + e * Np * 6;
+        mbar_wait(barY, par);
+
+        double acc[3][NT][2];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++) acc[c][nt][0] = acc[c][nt][1] = 0.0;
+
+        // ---------------- face (e, j): where the exterior trace comes from; first neighbour record requested now -----------
+        const int2 info = wDesc[e * 4 + j];
+        const int code = info.y;
+        const double *nbase = yrec;
+        uint4 nrow = ownrow;
+        double ce = 0.0, ch = 0.0, al = A.alpha;
+        if (info.x >= 0) {
+            nrow = sTab[(code >> FI_TAB_SHIFT) & FI_TAB_MASK];
+            nbase = (info.x >> 3) == g ? wY + (info.x & 7) * Np * 6 : A.yin + (size_t)info.x * Np * 6;
+        } else if (info.x == -1) {
+            const int bc = code & FI_BC_MASK;
+            ce = bc == 1 ? -2.0 : bc == 3 ? -1.0 : 0.0;
+            ch = bc == 2 ? -2.0 : bc == 3 ? -1.0 : 0.0;
+            if (bc == 3) al = 1.0;
+        } else {
+            nrow = sTab[4 + j];
+            nbase = A.halo + (size_t)(-2 - info.x) * Nfp * 6;
+        }
+        if (!halo_ready && __any_sync(0xffffffffu, info.x < -1)) { p2p_wait(A.pp, lane); halo_ready = true; }
+        double uQ[PF + 1][6];
+#pragma unroll
+        for (int q = 0; q < PF; q++) load_rec(nbase + tab_byte(nrow, q) * 6, uQ[q]);
+
+        // ---------------- volume: my field's k~_c = D_{c+1} u~_{c+2} - D_{c+2} u~_{c+1} of the OTHER field ---------------------
+        {
+            double jm[9];
+#pragma unroll
+            for (int i = 0; i < 9; i++) jm[i] = sgn * ge[i];
+#pragma unroll
+            for (int ks = 0; ks < KSV; ks++) {
+                const int node = 4 * ks + j;
+                double u[3] = {0, 0, 0};
+                if (4 * ks + 3 < Np || node < Np) load3(yrec + node * 6 + oth, u);
+                double ut[3];
+#pragma unroll
+                for (int a = 0; a < 3; a++) ut[a] = fma(jm[a], u[0], fma(jm[3 + a], u[1], jm[6 + a] * u[2]));
+                const double *fr = sFragV + (ks * VT) * 32 + lane;
+#pragma unroll
+                for (int nt = 0; nt < NT - 1; nt++)
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        const double bv = fr[(nt * 3 + d) * 32];
+                        const int cp = (d + 2) % 3, cm = (d + 1) % 3;
+                        dmma884(acc[cp][nt][0], acc[cp][nt][1], ut[(d + 1) % 3], bv);
+                        dmma884(acc[cm][nt][0], acc[cm][nt][1], -ut[(d + 2) % 3], bv);
+                    }
+#pragma unroll
+                for (int x = 0; x < 3; x++) {
+                    const double bv = fr[((NT - 1) * 3 + x) * 32];
+                    dmma884(acc[x][NT - 1][0], acc[x][NT - 1][1], ut[x], bv);
+                }
+            }
+        }
+        if ((LOAD_X || LOAD_Z) && it > 0 && leader) { bulk_wait_read(); issue_xz(g); }
+
+        // ---------------- face flux of (element e, face j), my field's rows -> LIFT ---------------------------------------------
+        {
+            const int tf = (code >> FI_TFSF_SHIFT) & FI_TFSF_MASK;
+            const double sOwn = 1.0 - (h ? ch : ce), sOth = 1.0 - (h ? ce : ch);   // dU = u+ - (1 - c) u-
+            double ji[9];
+#pragma unroll
+            for (int i = 0; i < 9; i++) ji[i] = ge[9 + i];
+            double gn[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) gn[d] = j == 0 ? (ji[d] + ji[3 + d]) + ji[6 + d] : -ji[3 * (j - 1) + d];
+            const double fs = ge[18 + j];
+            const double ifs = 1.0 / fs, ifs2 = ifs * ifs;
+            const double af = al * fs;
+            // F~_own = Ae dU_own + Ax dU_other, Ax = +J^-1 [n x] for the E rows, -J^-1 [n x] for the H rows
+            double Ax[9], Ae[9];
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                const double j0 = ji[3 * a], j1 = ji[3 * a + 1], j2 = ji[3 * a + 2];
+                Ax[3 * a + 0] = sgn * (j1 * gn[2] - j2 * gn[1]);
+                Ax[3 * a + 1] = sgn * (j2 * gn[0] - j0 * gn[2]);
+                Ax[3 * a + 2] = sgn * (j0 * gn[1] - j1 * gn[0]);
+                const double w = (j0 * gn[0] + j1 * gn[1] + j2 * gn[2]) * ifs2;
+                Ae[3 * a + 0] = af * (j0 - w * gn[0]);
+                Ae[3 * a + 1] = af * (j1 - w * gn[1]);
+                Ae[3 * a + 2] = af * (j2 - w * gn[2]);
+            }
+#pragma unroll
+            for (int s = 0; s < Nfp; s++) {
+                const double *uP = uQ[s % (PF + 1)];
+                const double *mrec = yrec + tab_byte(ownrow, s) * 6;
+                double mO[3], mX[3], dO[3], dX[3];
+                load3(mrec + own, mO);
+                load3(mrec + oth, mX);
+                if (s + PF < Nfp) load_rec(nbase + tab_byte(nrow, s + PF) * 6, uQ[(s + PF) % (PF + 1)]);
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const double pO = h ? uP[3 + c] : uP[c], pX = h ? uP[c] : uP[3 + c];
+                    dO[c] = fma(-sOwn, mO[c], pO);
+                    dX[c] = fma(-sOth, mX[c], pX);
+                }
+                if (TF && tf && inject) {
+                    double inc[6];
+                    const int m = tab_byte(sTab[4 + j], s);
+                    planewave6(A.pw, A.tfsf_xyz + ((long long)(code >> FI_TIDX_SHIFT) * Nfp + m) * 3, A.t, inc);
+                    const double sg = tf == 1 ? 1.0 : -1.0;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) { dO[c] += sg * (h ? inc[3 + c] : inc[c]); dX[c] += sg * (h ? inc[c] : inc[3 + c]); }
+                }
+                double ft[3];
+#pragma unroll
+                for (int a = 0; a < 3; a++)
+                    ft[a] = fma(Ae[3 * a + 2], dO[2], fma(Ae[3 * a + 1], dO[1], fma(Ae[3 * a], dO[0],
+                            fma(Ax[3 * a + 2], dX[2], fma(Ax[3 * a + 1], dX[1], Ax[3 * a] * dX[0])))));
+                const double *fr = sFragL + (s * NT) * 32 + lane;
+#pragma unroll
+                for (int nt = 0; nt < NT - 1; nt++) {
+                    const double bv = fr[nt * 32];
+#pragma unroll
+                    for (int c = 0; c < 3; c++) dmma884(acc[c][nt][0], acc[c][nt][1], ft[c], bv);
+                }
+                {
+                    const double bv = fr[(NT - 1) * 32];
+#pragma unroll
+                    for (int c = 0; c < 3; c++) dmma884(acc[(c + 2) % 3][NT - 1][0], acc[(c + 2) % 3][NT - 1][1], ft[c], bv);
+                }
+            }
+        }
+
+        // ---------------- push forward, material, Runge-Kutta stage (my three components of every record) -------------------
+        double jm[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) jm[i] = ge[i];
+        const double dmat = h ? ge[24] : ge[23];            // det/mu : det/eps
+        const double se = h ? 0.0 : ge[25];                 // sigma/eps acts on E only
+        const bool keep_y = A.has_sigma != 0;
+        const int gnext = g + gstride;
+        if (!keep_y) {
+            pair_sync(1 + gs);                              // both warps have read y_in for the last time
+            if (leader && gnext < A.ngroups) issue_y(gnext);
+        }
+        if (LOAD_X || LOAD_Z) mbar_wait(barXZ, par);
+        const bool plain = keep_y || MODE == MODE_MULT;
+        const double ca = plain ? A.a : A.a * dmat, cb = plain ? A.b : A.b * dmat;
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                const int node = nt < NT - 1 ? 8 * nt + j + 4 * hh : 8 * (NT - 1) + j;
+                if (nt == NT - 1 && hh == 1) continue;
+                if (nt == NT - 1 && NL < 4 && j >= NL) continue;
+                double kr[3];
+                if (nt < NT - 1) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) kr[c] = acc[c][nt][hh];
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) kr[c] = acc[(c + 2) % 3][NT - 1][0] + acc[(c + 1) % 3][NT - 1][1];
+                }
+                double k[3];
+#pragma unroll
+                for (int d = 0; d < 3; d++) k[d] = fma(jm[3 * d], kr[0], fma(jm[3 * d + 1], kr[1], jm[3 * d + 2] * kr[2]));
+                const int off = (e * Np + node) * 6 + own;
+                if (plain) {
+                    double uo[3] = {0, 0, 0};
+                    if (keep_y) load3(wY + off, uo);
+#pragma unroll
+                    for (int d = 0; d < 3; d++) k[d] = fma(dmat, k[d], -(se * uo[d]));
+                }
+                double xv[3], zv[3], o[3], zn[3];
+                if (LOAD_X) load3(wX + off, xv);
+                if (LOAD_Z) load3(wZ + off, zv);
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    if (MODE == MODE_MULT) o[c] = k[c];
+                    else if (MODE == MODE_STAGE1) { o[c] = fma(ca, k[c], xv[c]); zn[c] = fma(cb, k[c], xv[c]); }
+                    else if (MODE == MODE_STAGE23) { o[c] = fma(ca, k[c], xv[c]); zn[c] = fma(cb, k[c], zv[c]); }
+                    else zn[c] = fma(cb, k[c], zv[c]);
+                }
+                if (STORE_X) store3(wX + off, o);
+                if (STORE_Z) store3(wZ + off, zn);
+            }
+        fence_async_smem();
+        pair_sync(1 + gs);                                  // complete records in wX / wZ
+        if (h == 0) {
+            if (MODE != MODE_MULT && A.pp.signal_epoch != 0 && info.x < -1) {
+                const int2 hp = A.pp.hpush[-2 - info.x];
+                const uint4 prow = sTab[hp.x >> 8];
+                double *dst = A.pp.peer_out[hp.x & 0xff] + (size_t)hp.y * Nfp * 6;
+                const double *src = (MODE == MODE_STAGE4 ? wZ : wX) + e * Np * 6;
+#pragma unroll
+                for (int m = 0; m < Nfp; m++) {
+                    double r[6];
+                    load_rec(src + tab_byte(prow, m) * 6, r);
+                    store_rec(dst + m * 6, r);
+                }
+            }
+            if (lane == 0) {
+                const size_t goff = (size_t)g * GS;
+                if (STORE_X) bulk_store(A.yout + goff, wX, GS * 8);
+                if (MODE == MODE_STAGE4) bulk_store(A.yout + goff, wZ, GS * 8);
+                else if (STORE_Z) bulk_store(A.z + goff, wZ, GS * 8);
+                bulk_commit();
+                if (keep_y && gnext < A.ngroups) issue_y(gnext);
+                if (!(LOAD_X || LOAD_Z)) bulk_wait_read();
+            }
+        }
+        if (!(LOAD_X || LOAD_Z)) pair_sync(1 + gs);         // Mult: the partner must not overwrite wX before the store has read it
+    }
+    if (leader) bulk_wait_all();
+    if (MODE != MODE_MULT && A.pp.signal_epoch != 0) p2p_signal(A.pp);
+}
+
+}  // namespace dgtd

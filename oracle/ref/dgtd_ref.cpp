@@ -720,6 +720,17 @@ static void initState(Vector &x, const std::string &spec, const std::vector<doub
          x[c * N + i] = v;
       }
    }
+   else if (q[0] == "smooth")
+   {
+      // smooth : all six components non-zero, reproducible from the node coordinates alone (tests/conftest.py:smooth_state):
+      // u_c = sin(1.3 x + 0.7 c + 0.2) cos(0.9 y - 0.4 c) + 0.5 sin(1.1 z + c)
+      for (int c = 0; c < 6; c++)
+         for (int i = 0; i < N; i++)
+         {
+            const double X = xyz[3 * (size_t)i], Y = dim > 1 ? xyz[3 * (size_t)i + 1] : 0.0, Z = dim > 2 ? xyz[3 * (size_t)i + 2] : 0.0;
+            x[c * N + i] = sin(1.3 * X + 0.7 * c + 0.2) * cos(0.9 * Y - 0.4 * c) + 0.5 * sin(1.1 * Z + c);
+         }
+   }
    else if (q[0] == "file") { auto v = slurp(q[1]); MFEM_VERIFY((int)v.size() == 6 * N, "x0 size"); for (int i = 0; i < 6 * N; i++) { x[i] = v[i]; } }
    else if (q[0] != "zero") { fprintf(stderr, "unknown init %s\n", spec.c_str()); exit(2); }
 }
@@ -919,7 +930,7 @@ int main(int argc, char **argv)
    {
       fprintf(stderr, "usage: dgtd_ref gen|bench --mesh <file|cart3d:n|cart2d:nx:ny|cart1d:n> [--refine r] --order p --alpha a\n"
               "          [--bdr a:pec,b:sma] [--bdr-all pec] [--tfsf t1,t2] [--pw spread:mean|auto:freq:px,py,pz:kx,ky,kz]\n"
-              "          [--mat a:eps:mu:sigma] [--init random:seed|gauss:E:c:s:fdim:cx,cy,cz|resonant:c:mx,my|file:path]\n"
+              "          [--mat a:eps:mu:sigma] [--init random:seed|gauss:E:c:s:fdim:cx,cy,cz|resonant:c:mx,my|smooth|file:path]\n"
               "          [--dt dt] [--steps k] [--warmup w] [--t0 t] [--snap 1,2] [--out dir] [--dump-csr]\n"
               "       dgtd_ref known-answers <records.txt> <Maxwell2D_K2.mesh>\n");
       return 2;

@@ -17,7 +17,49 @@ def pytest_configure(config):
 
 
 def golden_cases():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not p.endswith(".cfg.npz"))
+
+
+def config_cases():
+    """Sampled reference vectors of BASELINE.json's configs on the reference's own meshes (make_config_fixtures.py)."""
+    return sorted(os.path.basename(p)[:-len(".cfg.npz")] for p in glob.glob(os.path.join(GOLDEN, "*.cfg.npz")))
+
+
+def smooth_state(xyz):
+    """`--init smooth` of oracle/ref/dgtd_ref.cpp: u_c = sin(1.3 x + 0.7 c + 0.2) cos(0.9 y - 0.4 c) + 0.5 sin(1.1 z + c)."""
+    x, y, z = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+    return np.concatenate([np.sin(1.3 * x + 0.7 * c + 0.2) * np.cos(0.9 * y - 0.4 * c) + 0.5 * np.sin(1.1 * z + c) for c in range(6)])
+
+
+def load_config_case(name):
+    """-> (oracle Problem, meta, dict of sampled arrays) for a *.cfg.npz fixture; the initial state comes from initial_state()."""
+    import json
+    from oracle.dgtd_oracle import BC_NAMES, PlaneWave, Problem
+
+    z = np.load(os.path.join(GOLDEN, name + ".cfg.npz"), allow_pickle=False)
+    meta = json.loads(str(z["meta"]))
+    pb = Problem(verts=z["verts_f64"].reshape(-1, 3), elems=z["elems_i32"].reshape(-1, 4).astype(np.int64), elem_attr=z["elem_attr_i32"],
+                 bdr=z["bdr_i32"].reshape(-1, 3).astype(np.int64), bdr_attr=z["bdr_attr_i32"], order=meta["order"], alpha=meta["alpha"])
+    pb.bdr_cond = {int(k): BC_NAMES[v] for k, v in meta.get("bdr", {}).items()}
+    pb.tfsf_tags = tuple(meta.get("tfsf", ()))
+    if meta.get("pw", {}).get("on"):
+        w = meta["pw"]
+        pb.planewave = PlaneWave(w["spread"], w["mean1d"], w["pol"], w["dir"], w["freq"])
+    return pb, meta, {k: z[k] for k in ("x0_sample_f64", "k0_sample_f64", "x_final_sample_f64")}
+
+
+def initial_state(meta, xyz):
+    """The fixture's initial condition, rebuilt from node coordinates [N][3]."""
+    if meta["init"] == "smooth":
+        return smooth_state(xyz)
+    kind, comp, modes = meta["init"].split(":")
+    assert kind == "resonant"
+    x0 = np.zeros((6, len(xyz)))
+    v = np.ones(len(xyz))
+    for k, m in enumerate(modes.split(",")):
+        v = v * np.sin(float(m) * np.pi * xyz[:, k])
+    x0[int(comp)] = v
+    return x0.ravel()
 
 
 def load_golden(name):

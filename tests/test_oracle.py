@@ -122,3 +122,27 @@ def test_energy_properties(name, alpha):
         assert abs(e) < 1e-11 * scale * 100
     else:
         assert e < 0
+
+
+@pytest.mark.parametrize("name", __import__("conftest").config_cases())
+def test_numpy_oracle_matches_reference_on_baseline_configs(name):
+    """BASELINE.json configs 3 and 4 on the reference's own meshes (22 400 / 15 886 tetrahedra): the portable oracle against
+    every 61st entry of the reference operator's Mult output and of the state after two mfem::RK4Solver steps."""
+    from conftest import initial_state, load_config_case
+    pb, meta, smp = load_config_case(name)
+    O = HesthavenOracle(pb)
+    assert O.N == meta["n"]
+    st = meta["stride"]
+    x0 = initial_state(meta, O.xyz.reshape(-1, 3))
+    assert rel_l2(x0[::st], smp["x0_sample_f64"]) < 1e-14
+    k = O.mult(meta["t0"], x0)
+    assert rel_l2(k[::st], smp["k0_sample_f64"]) < 1e-12
+    assert abs(np.linalg.norm(k) / meta["k0_norm"] - 1.0) < 1e-12
+    x, t = x0, meta["t0"]
+    for _ in range(meta["steps"]):
+        x = O.rk4_step(x, t, meta["dt"])
+        t += meta["dt"]
+    assert rel_l2(x[::st], smp["x_final_sample_f64"]) < 1e-12
+    assert abs(np.linalg.norm(x) / meta["x_final_norm"] - 1.0) < 1e-12
+    if meta.get("tfsf"):
+        assert meta["tfsf_applied"] > 0          # the plane wave is on the TF/SF surface at t0
