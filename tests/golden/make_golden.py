@@ -112,6 +112,12 @@ def two_material_mesh(path):
 if __name__ == "__main__":
     if not os.path.exists(REF):
         sys.exit("build oracle/_ref first: make -C oracle/ref")
+    if len(sys.argv) > 1 and sys.argv[1] == "config2":
+        # config 2 of BASELINE.json on the reference's own gmsh triangle mesh: 2D_PEC.json (246 triangles, order 3, upwind,
+        # global operator, PEC on tags 2,4 and PMC on 1,3, Gaussian E_z of spread 0.12 varying along x, dt 1e-3)
+        run("config2_2d_pec_p3", "--mesh /root/reference/testData/maxwellInputs/2D_PEC/2D_PEC.msh --order 3 --alpha 1.0 --bdr 1:pmc,2:pec,3:pmc,4:pec "
+            "--init gauss:E:2:0.12:1:0.5,0.5 --dt 1e-3 --steps 20".split(), {"bdr": {"1": "pmc", "2": "pec", "3": "pmc", "4": "pec"}})
+        sys.exit(0)
     run("box3d_p3_pec_upwind", "--mesh cart3d:2 --order 3 --alpha 1.0 --bdr-all pec --init random:1 --dt 1e-3 --steps 2".split(),
         {"bdr": {str(a): "pec" for a in range(1, 7)}})
     run("box3d_p2_mixed_centered", "--mesh cart3d:2 --order 2 --alpha 0.0 --bdr 1:pec,2:pmc,3:pec,4:pmc,5:pec,6:pmc --init random:4 --dt 1e-3 --steps 2".split(),
