@@ -289,6 +289,12 @@ class Evolution:
         _ck(lib.dgtd_rk4_run(self._h, C.c_double(t0), C.c_double(dt), int(nsteps)))
         return t0 + nsteps * dt
 
+    def run_until(self, t0, dt, t_final, check_every=0):
+        """maxwell::Solver::run: steps of min(dt, t_final - t) until t_final -> (t, nsteps, unstable)."""
+        t, n, bad = C.c_double(t0), C.c_longlong(), C.c_int()
+        _ck(lib.dgtd_run_until(self._h, C.byref(t), C.c_double(dt), C.c_double(t_final), int(check_every), C.byref(n), C.byref(bad)))
+        return t.value, n.value, bool(bad.value)
+
     def synchronize(self):
         _ck(lib.dgtd_synchronize(self._h))
 

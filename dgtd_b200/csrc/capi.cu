@@ -820,6 +820,34 @@ int dgtd_rk4_run(dgtd_ctx *c, double t0, double dt, int nsteps)
     for (int s = 0; s < nsteps; s++) { rk4_step(c, t, dt); t += dt; }
     GUARD_END
 }
+int dgtd_run_until(dgtd_ctx *c, double *t, double dt, double t_final, int check_every, long long *nsteps, int *unstable)
+{
+    GUARD_BEGIN
+    if (!c || !t || !(dt > 0) || check_every < 0) throw Error(DGTD_ERR_ARG, "dgtd_run_until: bad argument");
+    CU(cudaSetDevice(c->device));
+    long long n = 0;
+    int bad = 0;
+    // Solver::run / Solver::step (Solver.cpp:497-551): while (time <= final - 1e-8 dt) { truedt = min(dt, final - time); Step; norm check }
+    while (*t <= t_final - 1e-8 * dt) {
+        const double truedt = std::min(dt, t_final - *t);
+        rk4_step(c, *t, truedt);
+        *t += truedt;
+        n++;
+        if (check_every && n % check_every == 0) {
+            double ss = 0;
+            CU(cudaMemsetAsync(c->scratch.p, 0, sizeof(double), c->stream));
+            sumsq_kernel<<<296, 256, 0, c->stream>>>(c->x.p, 6 * c->Nalloc, c->scratch.p);
+            c->launches++;
+            CU(cudaMemcpyAsync(&ss, c->scratch.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            const double nrm = std::sqrt(ss);
+            if (!std::isfinite(nrm) || nrm > 1e20) { bad = 1; break; }   // the reference warns and goes on; here the caller decides
+        }
+    }
+    if (nsteps) *nsteps = n;
+    if (unstable) *unstable = bad;
+    GUARD_END
+}
 int dgtd_norm2_local(dgtd_ctx *c, double *sumsq)
 {
     GUARD_BEGIN

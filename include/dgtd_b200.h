@@ -130,6 +130,11 @@ int  dgtd_mult(dgtd_ctx *, double t, const double *in, double *out, int on_devic
 int  dgtd_rk4_step(dgtd_ctx *, double t, double dt);
 /* nsteps of the above from t0 (Solver::run loop body, Solver.cpp:483-533, without probes)         */
 int  dgtd_rk4_run(dgtd_ctx *, double t0, double dt, int nsteps);
+/* Solver::run (Solver.cpp:497-533) with Solver::step's final short step (Solver.cpp:535-537): advances *t from its value
+ * to t_final with steps of min(dt, t_final - t).  check_every > 0 evaluates the reference's per-step stability test
+ * (!isfinite(norm) || norm > 1e20, Solver.cpp:500-516) on this rank's dofs every that many steps and stops with
+ * *unstable = 1 when it fires (multi-rank callers reduce the flag as the reference does with MPI_MAX).            */
+int  dgtd_run_until(dgtd_ctx *, double *t, double dt, double t_final, int check_every, long long *nsteps, int *unstable);
 /* ||state||_2 over all ranks' owned dofs of THIS rank (caller reduces) — Fields::getNorml2        */
 int  dgtd_norm2_local(dgtd_ctx *, double *sumsq);
 /* point probes: field values at npts (local element, Np shape weights) -> out[npts][6]            */

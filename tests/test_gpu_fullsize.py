@@ -127,3 +127,27 @@ def test_pec_cavity_mode_follows_the_analytic_solution(dg, alpha):
     # the numpy oracle gives 2.7e-2 / 1.7e-3 (upwind) and 5.6e-2 / 5.2e-3 (centred) at 2^3 / 4^3 cubes: order h^4 and ~h^3.5
     assert err < (2e-5 if alpha == 1.0 else 2e-4), err
     ev.close()
+
+
+def test_run_until_follows_the_reference_time_loop(dg):
+    """Solver::run / Solver::step (Solver.cpp:497-551): steps of min(dt, T - t) while t <= T - 1e-8 dt, stability test on
+    the state norm."""
+    ev = _box(dg, 4)
+    rng = np.random.default_rng(2)
+    x0 = rng.standard_normal(6 * ev.N) * 1e-2
+    dt, T = 1.0e-3, 0.0105                      # 10 full steps and one of half the size
+    ev.set_state(x0)
+    t, n, bad = ev.run_until(0.0, dt, T, check_every=1)
+    assert n == 11 and not bad and abs(t - T) < 1e-15
+    a = ev.get_state()
+    ev.set_state(x0)
+    tt = 0.0
+    for _ in range(10):
+        tt = ev.Step(tt, dt)
+    ev.Step(tt, T - tt)
+    assert np.array_equal(a, ev.get_state())
+    # far beyond the RK4 stability limit: the norm test must fire and stop the loop
+    ev.set_state(x0)
+    t, n, bad = ev.run_until(0.0, 0.5, 200.0, check_every=1)
+    assert bad and n < 400
+    ev.close()

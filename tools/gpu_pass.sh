@@ -10,7 +10,7 @@ nproc >> $OUT/smi.txt
 timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu.log
 tail -3 $OUT/pytest_gpu.log
 timeout 600 python bench.py --steps 20 --warmup 3 > $OUT/bench_default.json 2> $OUT/bench_default.err; tail -c 1500 $OUT/bench_default.json
-for K in ws mma; do
+for K in ws mma generic; do
 DGTD_B200_KERNEL=$K timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu > $OUT/bench_$K.json 2> $OUT/bench_$K.err; tail -c 600 $OUT/bench_$K.json
 done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 > $OUT/ncu_launches.log 2>&1
