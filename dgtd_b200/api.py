@@ -145,9 +145,10 @@ class Mesh:
         _ck(lib.dgtd_mesh_boundary_elements(self._h, len(a), _ip(a), C.c_longlong(n.value), _ip(pairs), C.byref(n)))
         return pairs
 
-    def partition(self, nranks):
+    def partition(self, nranks, method="rcb"):
+        """element -> rank: "rcb" (coordinate bisection, the default of Evolution) or "metis" (k-way on the dual graph)."""
         p = np.zeros(self.ne, np.int32)
-        _ck(lib.dgtd_mesh_partition(self._h, nranks, _ip(p)))
+        _ck((lib.dgtd_mesh_partition_metis if method == "metis" else lib.dgtd_mesh_partition)(self._h, nranks, _ip(p)))
         return p
 
     def __del__(self):

@@ -602,6 +602,14 @@ int dgtd_mesh_partition(const dgtd_mesh *m, int nranks, int *partitioning)
     std::memcpy(partitioning, p.data(), p.size() * sizeof(int));
     GUARD_END
 }
+int dgtd_mesh_partition_metis(const dgtd_mesh *m, int nranks, int *partitioning)
+{
+    GUARD_BEGIN
+    if (!m || !partitioning) throw Error(DGTD_ERR_ARG, "null argument");
+    auto p = partition_metis(m->m, nranks);
+    std::memcpy(partitioning, p.data(), p.size() * sizeof(int));
+    GUARD_END
+}
 void dgtd_mesh_destroy(dgtd_mesh *m) { delete m; }
 
 int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)

@@ -30,6 +30,7 @@ struct Mesh {
 Mesh load_mesh(const std::string &path);
 Mesh cartesian3d(int nx, int ny, int nz, double sx, double sy, double sz);
 std::vector<int> partition_rcb(const Mesh &m, int nranks);
+std::vector<int> partition_metis(const Mesh &m, int nranks);      // k-way on the element dual graph (the reference's partitioner)
 
 // Reference element on the unit simplex with MFEM's L2 Gauss-Lobatto nodes.
 struct RefElem {

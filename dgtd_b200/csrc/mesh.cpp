@@ -224,4 +224,46 @@ std::vector<int> partition_rcb(const Mesh &m, int nranks)
     return part;
 }
 
+// ---- METIS k-way partition of the element dual graph — what the reference does through
+// Mesh::GeneratePartitioning (src/driver/driver.cpp:1269; external/mfem-geg/mesh/mesh.cpp:8378 -> METIS_PartGraphKway).
+// The METIS here is the static library that ships in the CUDA toolkit (for cuSOLVER; 64-bit idx_t, no header installed),
+// so its two entry points are declared by hand; real_t arguments are passed as NULL (defaults).
+extern "C" {
+int METIS_SetDefaultOptions(long long *options);
+int METIS_PartGraphKway(long long *nvtxs, long long *ncon, long long *xadj, long long *adjncy, long long *vwgt, long long *vsize,
+                        long long *adjwgt, long long *nparts, void *tpwgts, void *ubvec, long long *options, long long *edgecut, long long *part);
+}
+
+std::vector<int> partition_metis(const Mesh &m, int nranks)
+{
+    if (nranks < 1) throw Error(-1, "nranks must be positive");
+    const int ne = m.ne(), nf = m.dim + 1;
+    std::vector<int> part(ne, 0);
+    if (nranks == 1) return part;
+    // dual graph: elements sharing a face
+    struct Key { int v[3]; int e; };
+    std::vector<Key> keys((size_t)ne * nf);
+    for (int e = 0; e < ne; e++) for (int f = 0; f < nf; f++) {
+        Key &k = keys[(size_t)e * nf + f];
+        k.v[0] = k.v[1] = k.v[2] = -1; k.e = e; int c = 0;
+        for (int q = 0; q < nf; q++) if (q != f) k.v[c++] = m.elems[(size_t)e * nf + q];
+        std::sort(k.v, k.v + m.dim);
+    }
+    std::sort(keys.begin(), keys.end(), [](const Key &a, const Key &b) { return std::lexicographical_compare(a.v, a.v + 3, b.v, b.v + 3); });
+    std::vector<std::vector<long long>> adj(ne);
+    for (size_t i = 0; i + 1 < keys.size(); i++) {
+        const Key &a = keys[i], &b = keys[i + 1];
+        if (a.v[0] == b.v[0] && a.v[1] == b.v[1] && a.v[2] == b.v[2]) { adj[a.e].push_back(b.e); adj[b.e].push_back(a.e); i++; }
+    }
+    std::vector<long long> xadj(ne + 1, 0), adjncy;
+    for (int e = 0; e < ne; e++) { adjncy.insert(adjncy.end(), adj[e].begin(), adj[e].end()); xadj[e + 1] = (long long)adjncy.size(); }
+    long long nv = ne, ncon = 1, np = nranks, cut = 0, options[40];
+    METIS_SetDefaultOptions(options);
+    std::vector<long long> p64(ne, 0);
+    const int rc = METIS_PartGraphKway(&nv, &ncon, xadj.data(), adjncy.data(), nullptr, nullptr, nullptr, &np, nullptr, nullptr, options, &cut, p64.data());
+    if (rc != 1) throw Error(-1, "METIS_PartGraphKway failed (" + std::to_string(rc) + ")");
+    for (int e = 0; e < ne; e++) part[e] = (int)p64[e];
+    return part;
+}
+
 }  // namespace dgtd

@@ -91,8 +91,12 @@ int  dgtd_mesh_cartesian3d(int nx, int ny, int nz, double sx, double sy, double 
 int  dgtd_mesh_info(const dgtd_mesh *, int *dim, int *nv, int *ne, int *nbe);
 /* copies out what dgtd_mesh_from_arrays takes in (any pointer may be NULL)                        */
 int  dgtd_mesh_get_arrays(const dgtd_mesh *, double *verts, int *elems, int *elem_attr, int *bdr, int *bdr_attr);
-/* element -> rank by recursive coordinate bisection of element barycentres (METIS is not in the image) */
+/* element -> rank by recursive coordinate bisection of element barycentres (slabs / bricks on Cartesian boxes; the default
+ * when dgtd_options.partitioning is NULL)                                                                         */
 int  dgtd_mesh_partition(const dgtd_mesh *, int nranks, int *partitioning);
+/* element -> rank by METIS k-way on the element dual graph, the reference's partitioner (Mesh::GeneratePartitioning,
+ * src/driver/driver.cpp:1269); hand the result to dgtd_options.partitioning                                          */
+int  dgtd_mesh_partition_metis(const dgtd_mesh *, int nranks, int *partitioning);
 void dgtd_mesh_destroy(dgtd_mesh *);
 
 /* ---- context = the evolution operator ----------------------------------------------------------- */

@@ -38,7 +38,8 @@ def main():
         pb, dat = load_golden(name)
         meta = dat["meta"]
         mesh, kw = product_mesh_and_kwargs(pb)
-        ev = dg.Evolution(mesh, device=local, rank=rank, nranks=world, **kw)
+        part = mesh.partition(world, "metis") if os.environ.get("DGTD_TEST_PARTITION") == "metis" else None   # None: built-in RCB
+        ev = dg.Evolution(mesh, device=local, rank=rank, nranks=world, partitioning=part, **kw)
         ev.comm_init(uid)
         N, Np = ev.N, ev.Np
         mine = np.zeros(N, bool)

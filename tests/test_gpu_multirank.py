@@ -22,7 +22,8 @@ def test_partitioned_run_matches_reference_vectors(world, halo):
     ncclSend/ncclRecv.  Both must reproduce the reference vectors on every rank's owned dofs."""
     if _ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
-    env = dict(os.environ, DGTD_B200_HALO=halo, DGTD_EXPECT_HALO_MODE="2" if halo == "p2p" else "1")
+    env = dict(os.environ, DGTD_B200_HALO=halo, DGTD_EXPECT_HALO_MODE="2" if halo == "p2p" else "1",
+               DGTD_TEST_PARTITION="metis" if halo == "p2p" else "rcb")      # METIS k-way parts with the fused halo, RCB slabs with NCCL
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(29400 + world + (10 if halo == "nccl" else 0)), os.path.join(ROOT, "tests", "mp_parity.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)

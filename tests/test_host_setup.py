@@ -162,8 +162,27 @@ def test_partitioner_and_halo_plan_two_ranks_in_process():
                     assert np.abs(mine - theirs).max() < 1e-14
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_direct_push_plan_is_consistent_across_ranks(world):
+def test_metis_partition_of_the_dual_graph():
+    """dgtd_mesh_partition_metis (the reference partitions with METIS, driver.cpp:1269): every rank owns a balanced,
+    non-empty share and the cut is no worse than coordinate bisection's on an unstructured-like case."""
+    pb, _, _ = __import__("conftest").load_config_case("config4_rcs_pec_p3")
+    mesh, kw = product_mesh_and_kwargs(pb)
+    elems = np.asarray(pb.elems)
+    faces = {}
+    for e, t in enumerate(elems.tolist()):
+        for k in range(4):
+            faces.setdefault(tuple(sorted(t[:k] + t[k + 1:])), []).append(e)
+    pairs = np.array([v for v in faces.values() if len(v) == 2])
+    cut = lambda p: int((p[pairs[:, 0]] != p[pairs[:, 1]]).sum())
+    for world in (2, 8):
+        pm, pr = mesh.partition(world, "metis"), mesh.partition(world, "rcb")
+        cnt = np.bincount(pm, minlength=world)
+        assert cnt.min() > 0 and cnt.max() <= 1.05 * len(elems) / world
+        assert cut(pm) <= cut(pr)
+
+
+@pytest.mark.parametrize("world,method", [(2, "rcb"), (4, "rcb"), (4, "metis")])
+def test_direct_push_plan_is_consistent_across_ranks(world, method):
     """Peer-memory halo path (kernels_wg.cuh: WgP2P): the slot a rank stores a face's traces into on its neighbour must be
     the slot the neighbour reads for that face, in the neighbour's face-node order; flag slots must be mutually consistent."""
     pb, _ = load_golden("box3d_p3_pec_upwind")
@@ -172,8 +191,9 @@ def test_direct_push_plan_is_consistent_across_ranks(world):
     Np, Nfp = O.Np, O.Nfp
     xyz = O.xyz.reshape(-1, 3)
     R = {}
+    part = mesh.partition(world, method)
     for r in range(world):
-        q = lambda name, dt: _q(mesh, kw, name, dt, rank=r, nranks=world)
+        q = lambda name, dt: _q(mesh, kw, name, dt, rank=r, nranks=world, partitioning=part)
         R[r] = dict(gid=q("elem_gid", np.int32), peers=q("peers5", np.int32).reshape(-1, 5), hpush=q("wg_hpush", np.int32).reshape(-1, 2),
                     tab=q("wg_tab", np.uint8).reshape(-1, 16), desc=q("wg_desc", np.int32).reshape(-1, 4, 2), d2r=q("wg_dev2ref", np.int32))
     for r in range(world):
