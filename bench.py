@@ -59,12 +59,47 @@ def ncu_traffic(kernel_info, dofs):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons sampled DURING the timed region: NVML queries every 2 ms (nvidia_ml_py), nvidia-smi
+    every 100 ms as fallback (one nvidia-smi call takes longer than a whole 20-step timed region)."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
-        self.max_mhz = None
+        self.index, self.samples, self.stamps, self.reasons, self.stop_flag = index, [], [], set(), False
+        self.window = None            # (t0, t1) of the timed region, perf_counter
+        self.max_mhz, self.how = None, "nvml"
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a list of ordinals
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [int(v) for v in vis.split(",") if v.strip().isdigit()]
+            phys = ids[index] if index < len(ids) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml, self.how = None, "nvidia-smi"
 
     def run(self):
+        if self.nvml is not None:
+            n = self.nvml
+            while not self.stop_flag:
+                try:
+                    self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                    self.stamps.append(time.perf_counter())
+                    try:
+                        mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                    except Exception:
+                        mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                    for name, bit in self.REASONS.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+                time.sleep(0.002)
+            return
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -73,16 +108,23 @@ class ClockSampler(threading.Thread):
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip().split(",")
                 self.samples.append(float(out[0])); self.max_mhz = float(out[1])
-                for n, v in zip(names, out[2:]):
+                self.stamps.append(time.perf_counter())
+                for nme, v in zip(names, out[2:]):
                     if v.strip().lower().startswith("active"):
-                        self.reasons.add(n)
+                        self.reasons.add(nme)
             except Exception:
                 pass
             time.sleep(0.1)
 
     def result(self):
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+        """Median SM clock of the samples taken inside the timed region; when the region is shorter than a few NVML
+        queries the samples of the whole loaded phase (warm-up .. end of the timed region) are reported beside it."""
+        allp = sorted(self.samples)
+        inw = sorted(v for v, t in zip(self.samples, self.stamps) if self.window and self.window[0] <= t <= self.window[1])
+        use = inw or allp
+        return {"sm_mhz": use[len(use) // 2] if use else None, "sm_min_mhz": use[0] if use else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(inw), "samples_under_load": len(allp),
+                "sm_mhz_under_load": allp[len(allp) // 2] if allp else None, "how": self.how}
 
 
 def cpu_reference(cubes, steps, warmup, threads=None):
@@ -198,20 +240,24 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     t = 0.0
     for _ in range(warm):
         t = ev.Step(t, dt)
     barrier()
     l0 = ev.launch_count()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    w0 = time.perf_counter()
     e0.record(stream)
     ev.run(t, dt, args.steps)
     e1.record(stream)
     barrier()
+    sampler.window = (w0, time.perf_counter())
+    if rank == 0:
+        sampler.stop_flag = True
     ms = e0.elapsed_time(e1)
     launches = ev.launch_count() - l0
     if rank == 0:

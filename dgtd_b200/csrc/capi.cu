@@ -153,23 +153,18 @@ static bool select_ws(int dim, int p, MmaSet &ms)
 // the warp-per-group kernel: tetrahedra of order 1..4, element-major "aos" layout, one warp per group of 8 elements
 typedef void (*WgFn)(const WgArgs);
 struct WgSet { WgFn fn[4]; int threads; size_t smem; };
-template <int P, int V, bool TF> static WgSet wgset()
+template <int P, bool TF> static WgSet wgset()
 {
     using B = Wg<P>;
-    return {{stage_wg_kernel<P, 0, V, TF>, stage_wg_kernel<P, 1, V, TF>, stage_wg_kernel<P, 2, V, TF>, stage_wg_kernel<P, 3, V, TF>}, B::T, B::smem_bytes};
+    return {{stage_wg_kernel<P, 0, TF>, stage_wg_kernel<P, 1, TF>, stage_wg_kernel<P, 2, TF>, stage_wg_kernel<P, 3, TF>}, B::T, B::smem_bytes};
 }
-template <int P> static WgSet wgset_p(int v, bool tf)
-{
-    if (v >= 3) return tf ? wgset<P, 3, true>() : wgset<P, 3, false>();
-    return tf ? wgset<P, 1, true>() : wgset<P, 1, false>();
-}
-// variants of kernels_wg.cuh: DGTD_B200_WGV=1|2 for A/B runs; tf = the context injects a TF/SF plane wave
-static bool select_wg(int dim, int p, int v, bool tf, WgSet &ws)
+// tf = the context injects a TF/SF plane wave
+static bool select_wg(int dim, int p, bool tf, WgSet &ws)
 {
     if (dim != 3) return false;
     switch (p) {
-        case 1: ws = wgset_p<1>(v, tf); return true; case 2: ws = wgset_p<2>(v, tf); return true;
-        case 3: ws = wgset_p<3>(v, tf); return true; case 4: ws = wgset_p<4>(v, tf); return true;
+        case 1: ws = tf ? wgset<1, true>() : wgset<1, false>(); return true; case 2: ws = tf ? wgset<2, true>() : wgset<2, false>(); return true;
+        case 3: ws = tf ? wgset<3, true>() : wgset<3, false>(); return true; case 4: ws = tf ? wgset<4, true>() : wgset<4, false>(); return true;
     }
     return false;
 }
@@ -197,7 +192,6 @@ struct dgtd_ctx {
     BlockedPlan BP;
     WgPlan WP;
     bool has_sigma = false;
-    int wgv = 1;                     // variant of the warp-per-group kernel (kernels_wg.cuh)
     bool wp = false;                 // ... or its warp-pair form (kernels_wp.cuh); wg stays set: same plan and layout
     int wg_groups_per_cta = 0;
     bool wg = false;                 // aos layout + warp-per-group kernel (blocked is set too: state needs layout conversion)
@@ -641,8 +635,6 @@ int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
     for (int le = 0; le < H.NEloc; le++) has_sigma |= H.geo[(size_t)le * GEO_STRIDE + 15] != 0.0;
     c->has_sigma = has_sigma;
     const bool tabs_ok = H.ntab <= 128;
-    const char *wgv = std::getenv("DGTD_B200_WGV");
-    c->wgv = wgv ? std::max(1, std::atoi(wgv)) : 1;
     const bool has_tf = H.pw.enabled && H.n_tfsf_faces > 0;
     // default: the warp-pair kernel at order 4 (8 instead of 4 warps per SM: 69 vs 60 G DOF-updates/s), the one-warp kernel
     // below it (at order 3 the pair's doubled fragment / trace loads make it shared-memory bound: 82 vs 110 G)
@@ -650,7 +642,7 @@ int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
         c->WP = build_wg_plan(H);
         if (c->WP.ntab <= Wg<3>::TABROWS) c->blocked = c->wg = c->wp = true;
     }
-    if (!c->wg && (ksel == "wg" || ksel == "wp" || ksel.empty()) && select_wg(H.dim, H.p, c->wgv, has_tf, c->wgs) && c->wgs.smem <= (size_t)prop.sharedMemPerBlockOptin) {
+    if (!c->wg && (ksel == "wg" || ksel == "wp" || ksel.empty()) && select_wg(H.dim, H.p, has_tf, c->wgs) && c->wgs.smem <= (size_t)prop.sharedMemPerBlockOptin) {
         c->WP = build_wg_plan(H);
         c->wg_groups_per_cta = c->wgs.threads / 32;
         if (c->WP.ntab <= Wg<3>::TABROWS) c->blocked = c->wg = true;
@@ -1003,8 +995,8 @@ int dgtd_kernel_info(const dgtd_ctx *c, char *buf, int cap)
         std::snprintf(tmp, sizeof tmp, "stage_wp_kernel<P=%d,MODE> DMMA m8n8k4 transposed, warp pair (E rows / H rows) per group of 8 elements, aos layout, %d threads, %zu B smem, grid %d%s",
                       c->H.p, c->wgs.threads, c->wgs.smem, c->grid, c->nranks == 1 ? "" : c->p2p ? ", halo: fused peer-memory stores" : ", halo: NCCL send/recv");
     else if (c->wg)
-        std::snprintf(tmp, sizeof tmp, "stage_wg_kernel<P=%d,MODE,V=%d> DMMA m8n8k4 transposed, warp per group of 8 elements, aos layout, %d threads, %zu B smem, grid %d%s",
-                      c->H.p, c->wgv, c->wgs.threads, c->wgs.smem, c->grid, c->nranks == 1 ? "" : c->p2p ? ", halo: fused peer-memory stores" : ", halo: NCCL send/recv");
+        std::snprintf(tmp, sizeof tmp, "stage_wg_kernel<P=%d,MODE> DMMA m8n8k4 transposed, warp per group of 8 elements, aos layout, %d threads, %zu B smem, grid %d%s",
+                      c->H.p, c->wgs.threads, c->wgs.smem, c->grid, c->nranks == 1 ? "" : c->p2p ? ", halo: fused peer-memory stores" : ", halo: NCCL send/recv");
     else if (c->blocked)
         std::snprintf(tmp, sizeof tmp, "%s<P=%d,G=%d,MODE> DMMA m8n8k4, blocked layout, %d threads, %zu B smem, grid %d",
                       c->ws ? "stage_ws_kernel" : "stage_mma_kernel", c->H.p, c->BP.G, c->ms.threads, c->ms.smem, c->grid);

@@ -134,33 +134,25 @@ __device__ __forceinline__ void load_rec(const double *p, double *u)
     const double2 a = q[0], b = q[1], c = q[2];
     u[0] = a.x; u[1] = a.y; u[2] = b.x; u[3] = b.y; u[4] = c.x; u[5] = c.y;
 }
-// the same as one asm-volatile statement: it keeps its place among the (volatile) DMMA statements, so a prefetch written
-// ahead of a contraction is issued ahead of it
-__device__ __forceinline__ void load_rec_pinned(const double *p, double *u)
-{
-    asm volatile("ld.v2.f64 {%0,%1}, [%6];\n\tld.v2.f64 {%2,%3}, [%6+16];\n\tld.v2.f64 {%4,%5}, [%6+32];"
-                 : "=d"(u[0]), "=d"(u[1]), "=d"(u[2]), "=d"(u[3]), "=d"(u[4]), "=d"(u[5]) : "l"(p));
-}
 __device__ __forceinline__ void store_rec(double *p, const double *u)
 {
     double2 *q = reinterpret_cast<double2 *>(p);
     q[0] = make_double2(u[0], u[1]); q[1] = make_double2(u[2], u[3]); q[2] = make_double2(u[4], u[5]);
 }
 
-// V = 0: neighbour traces prefetched one face step ahead, flux in physical components then pulled back with J^-1.
-// V >= 1: the first PF neighbour records are requested BEFORE the volume contraction (their L2 latency hides behind it),
-//        the prefetch runs PF = 2 steps ahead, and the flux is one 6x6 map per (element, face):
-//        F~_E = Ah dH + Ae dE, F~_H = -Ah dE + Ae dH with Ah = J^-1 [n x], Ae = alpha fs J^-1 (I - n n^T / fs^2).
-// V = 3: the neighbour-record loads are asm-volatile (pinned between the DMMA statements where they are written); measured
-//        equal to V = 1.  (Pulling the neighbour records into L1 with prefetch.global.L1 was measured 9 % slower.)
+// The first PF neighbour records of a face are requested BEFORE the volume contraction (their L2 latency hides behind it)
+// and the prefetch then runs PF face steps ahead; the flux is one 6x6 map per (element, face):
+//   F~_E = Ah dH + Ae dE,  F~_H = -Ah dE + Ae dH,  Ah = J^-1 [n x],  Ae = alpha fs J^-1 (I - n n^T / fs^2).
+// Measured alternatives (profiles/): one-step prefetch issued inside the face loop with the flux in physical
+// components, 97.9 G vs 110 G; asm-volatile (pinned) prefetch loads, +-0; prefetch.global.L1 of the records, -9 %.
 // TF: the context has a TF/SF plane-wave source (the injection code sits in the face loop only then).
-template <int P, int MODE, int V, bool TF>
+template <int P, int MODE, bool TF>
 __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
 {
     using B = Wg<P>;
     constexpr int Np = B::Np, Nfp = B::Nfp, NT = B::NT, KSV = B::KSV, VT = B::VT, GS = B::GS;
     constexpr int NL = Np - 8 * (NT - 1);                                          // nodes of the mixed tile
-    constexpr int PF = (V == 0 || P >= 4) ? 1 : 2;                                   // neighbour-record prefetch distance (face steps)
+    constexpr int PF = P >= 4 ? 1 : 2;                                             // neighbour-record prefetch distance (face steps)
     constexpr bool LOAD_X = MODE == MODE_STAGE1 || MODE == MODE_STAGE23;           // stage 1: x == y_in, fetched again (L2 hit)
     constexpr bool LOAD_Z = MODE == MODE_STAGE23 || MODE == MODE_STAGE4;
     constexpr bool STORE_X = MODE != MODE_STAGE4, STORE_Z = MODE != MODE_MULT;      // stage 4 forms the new x in the z buffer
@@ -239,13 +231,8 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
         }
         if (!halo_ready && __any_sync(0xffffffffu, info.x < -1)) { p2p_wait(A.pp, lane); halo_ready = true; }
         double uQ[PF + 1][6];
-        if (V != 0) {
 #pragma unroll
-            for (int q = 0; q < PF; q++) {
-                if (V >= 3) load_rec_pinned(nbase + tab_byte(nrow, q) * 6, uQ[q]);
-                else load_rec(nbase + tab_byte(nrow, q) * 6, uQ[q]);
-            }
-        }
+        for (int q = 0; q < PF; q++) load_rec(nbase + tab_byte(nrow, q) * 6, uQ[q]);
 
         // ---------------- volume: k~E_c = D_{c+1} u~H_{c+2} - D_{c+2} u~H_{c+1},  k~H likewise from u~E = -J^T E / det ------
         {
@@ -301,30 +288,23 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
             const double ifs = 1.0 / fs, ifs2 = ifs * ifs;
             const double af = al * fs;
             double Ah[9], Ae[9];
-            if (V != 0) {
 #pragma unroll
-                for (int a = 0; a < 3; a++) {
-                    const double j0 = ji[3 * a], j1 = ji[3 * a + 1], j2 = ji[3 * a + 2];
-                    Ah[3 * a + 0] = j1 * gn[2] - j2 * gn[1];
-                    Ah[3 * a + 1] = j2 * gn[0] - j0 * gn[2];
-                    Ah[3 * a + 2] = j0 * gn[1] - j1 * gn[0];
-                    const double w = (j0 * gn[0] + j1 * gn[1] + j2 * gn[2]) * ifs2;
-                    Ae[3 * a + 0] = af * (j0 - w * gn[0]);
-                    Ae[3 * a + 1] = af * (j1 - w * gn[1]);
-                    Ae[3 * a + 2] = af * (j2 - w * gn[2]);
-                }
-            } else {
-                load_rec(nbase + tab_byte(nrow, 0) * 6, uQ[0]);
+            for (int a = 0; a < 3; a++) {
+                const double j0 = ji[3 * a], j1 = ji[3 * a + 1], j2 = ji[3 * a + 2];
+                Ah[3 * a + 0] = j1 * gn[2] - j2 * gn[1];
+                Ah[3 * a + 1] = j2 * gn[0] - j0 * gn[2];
+                Ah[3 * a + 2] = j0 * gn[1] - j1 * gn[0];
+                const double w = (j0 * gn[0] + j1 * gn[1] + j2 * gn[2]) * ifs2;
+                Ae[3 * a + 0] = af * (j0 - w * gn[0]);
+                Ae[3 * a + 1] = af * (j1 - w * gn[1]);
+                Ae[3 * a + 2] = af * (j2 - w * gn[2]);
             }
 #pragma unroll
             for (int s = 0; s < Nfp; s++) {
                 double uM[6], dU[6];
                 const double *uP = uQ[s % (PF + 1)];
                 load_rec(yrec + tab_byte(ownrow, s) * 6, uM);
-                if (s + PF < Nfp) {
-                    if (V >= 3) load_rec_pinned(nbase + tab_byte(nrow, s + PF) * 6, uQ[(s + PF) % (PF + 1)]);
-                    else load_rec(nbase + tab_byte(nrow, s + PF) * 6, uQ[(s + PF) % (PF + 1)]);
-                }
+                if (s + PF < Nfp) load_rec(nbase + tab_byte(nrow, s + PF) * 6, uQ[(s + PF) % (PF + 1)]);
 #pragma unroll
                 for (int c = 0; c < 3; c++) { dU[c] = fma(-se1, uM[c], uP[c]); dU[3 + c] = fma(-sh1, uM[3 + c], uP[3 + c]); }   // u+ - u- (+ c u-)
                 if (TF && tf && inject) {
@@ -336,29 +316,12 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
                     for (int c = 0; c < 6; c++) dU[c] += sg * inc[c];
                 }
                 double ft[6];
-                if (V != 0) {
 #pragma unroll
-                    for (int a = 0; a < 3; a++) {
-                        ft[a] = fma(Ae[3 * a + 2], dU[2], fma(Ae[3 * a + 1], dU[1], fma(Ae[3 * a], dU[0],
-                                fma(Ah[3 * a + 2], dU[5], fma(Ah[3 * a + 1], dU[4], Ah[3 * a] * dU[3])))));
-                        ft[3 + a] = fma(Ae[3 * a + 2], dU[5], fma(Ae[3 * a + 1], dU[4], fma(Ae[3 * a], dU[3],
-                                    -fma(Ah[3 * a + 2], dU[2], fma(Ah[3 * a + 1], dU[1], Ah[3 * a] * dU[0])))));
-                    }
-                } else {
-                    const double gdE = (gn[0] * dU[0] + gn[1] * dU[1] + gn[2] * dU[2]) * ifs2;
-                    const double gdH = (gn[0] * dU[3] + gn[1] * dU[4] + gn[2] * dU[5]) * ifs2;
-                    double fl[6];
-                    fl[0] = (gn[1] * dU[5] - gn[2] * dU[4]) + af * (dU[0] - gdE * gn[0]);
-                    fl[1] = (gn[2] * dU[3] - gn[0] * dU[5]) + af * (dU[1] - gdE * gn[1]);
-                    fl[2] = (gn[0] * dU[4] - gn[1] * dU[3]) + af * (dU[2] - gdE * gn[2]);
-                    fl[3] = -(gn[1] * dU[2] - gn[2] * dU[1]) + af * (dU[3] - gdH * gn[0]);
-                    fl[4] = -(gn[2] * dU[0] - gn[0] * dU[2]) + af * (dU[4] - gdH * gn[1]);
-                    fl[5] = -(gn[0] * dU[1] - gn[1] * dU[0]) + af * (dU[5] - gdH * gn[2]);
-#pragma unroll
-                    for (int a = 0; a < 3; a++) {
-                        ft[a] = fma(ji[3 * a], fl[0], fma(ji[3 * a + 1], fl[1], ji[3 * a + 2] * fl[2]));
-                        ft[3 + a] = fma(ji[3 * a], fl[3], fma(ji[3 * a + 1], fl[4], ji[3 * a + 2] * fl[5]));
-                    }
+                for (int a = 0; a < 3; a++) {
+                    ft[a] = fma(Ae[3 * a + 2], dU[2], fma(Ae[3 * a + 1], dU[1], fma(Ae[3 * a], dU[0],
+                            fma(Ah[3 * a + 2], dU[5], fma(Ah[3 * a + 1], dU[4], Ah[3 * a] * dU[3])))));
+                    ft[3 + a] = fma(Ae[3 * a + 2], dU[5], fma(Ae[3 * a + 1], dU[4], fma(Ae[3 * a], dU[3],
+                                -fma(Ah[3 * a + 2], dU[2], fma(Ah[3 * a + 1], dU[1], Ah[3 * a] * dU[0])))));
                 }
                 const double *fr = sFragL + (s * NT) * 32 + lane;
 #pragma unroll
