@@ -2,7 +2,7 @@
 // elements carried by TWO warps that share the group's shared-memory buffers — warp role h = 0 forms the E rows of the
 // stage (k_E from u~_H and the E flux), h = 1 the H rows.
 //
-// Why (profiles/r1_wgv1_stage_ncu_summary.txt, tools: DGTD_WG_NW sweep): the one-warp kernel keeps 72 accumulator registers
+// Why (profiles/r1_final_stage_wg_ncu_summary.txt, tools: DGTD_WG_NW sweep): the one-warp kernel keeps 72 accumulator registers
 // and 25 KB of buffers per warp, so 8 warps fill an SM (2 per scheduler) and the FP64 pipe idles 28 % of the time on
 // latencies nobody covers (4 -> 8 warps per SM bought +35 %).  Halving the accumulator set per warp (36 registers at order
 // 3) lets 12 warps (3 per scheduler, 6 groups in flight) fit the register file at order 3, and 8 instead of 4 warps at
