@@ -262,7 +262,9 @@ std::vector<int> partition_metis(const Mesh &m, int nranks)
     std::vector<long long> p64(ne, 0);
     const int rc = METIS_PartGraphKway(&nv, &ncon, xadj.data(), adjncy.data(), nullptr, nullptr, nullptr, &np, nullptr, nullptr, options, &cut, p64.data());
     if (rc != 1) throw Error(-1, "METIS_PartGraphKway failed (" + std::to_string(rc) + ")");
-    for (int e = 0; e < ne; e++) part[e] = (int)p64[e];
+    std::vector<int> count(nranks, 0);
+    for (int e = 0; e < ne; e++) { part[e] = (int)p64[e]; count[part[e]]++; }
+    for (int r = 0; r < nranks; r++) if (count[r] == 0) return partition_rcb(m, nranks);   // tiny graphs: METIS may leave a part empty
     return part;
 }
 

@@ -33,10 +33,24 @@ def main():
         return bytes(idt.cpu().numpy().tobytes())
 
     worst = 0.0
-    for name in sys.argv[1:] or ["box3d_p3_pec_upwind", "tfsf3d_p2_on", "box3d_p4_sma_partial"]:
+    for name in sys.argv[1:] or ["box3d_p3_pec_upwind", "tfsf3d_p2_on", "box3d_p4_sma_partial", "config4_rcs_pec_p3"]:
         uid = fresh_unique_id()
-        pb, dat = load_golden(name)
-        meta = dat["meta"]
+        if name.startswith("config") and name.endswith(("p3", "p4")) and os.path.exists(os.path.join(ROOT, "tests", "golden", name + ".cfg.npz")):
+            # BASELINE config on the reference's own unstructured mesh (15 886 tets, several neighbours per rank): the
+            # reference vectors are the portable oracle's, itself pinned on the sampled reference output (tests/test_oracle.py)
+            from conftest import initial_state, load_config_case
+            from oracle.dgtd_oracle import HesthavenOracle
+            pb, meta, _ = load_config_case(name)
+            O = HesthavenOracle(pb)
+            x0 = initial_state(meta, O.xyz.reshape(-1, 3))
+            xf, tt = x0, meta["t0"]
+            for _ in range(meta["steps"]):
+                xf = O.rk4_step(xf, tt, meta["dt"])
+                tt += meta["dt"]
+            dat = {"x0_f64": x0, "k0_f64": O.mult(meta["t0"], x0), "x_final_f64": xf}
+        else:
+            pb, dat = load_golden(name)
+            meta = dat["meta"]
         mesh, kw = product_mesh_and_kwargs(pb)
         part = mesh.partition(world, "metis") if os.environ.get("DGTD_TEST_PARTITION") == "metis" else None   # None: built-in RCB
         ev = dg.Evolution(mesh, device=local, rank=rank, nranks=world, partitioning=part, **kw)
@@ -74,7 +88,7 @@ def main():
         err = torch.tensor([e_mult, e_run], dtype=torch.float64, device="cuda")
         dist.all_reduce(err, op=dist.ReduceOp.MAX)
         if rank == 0:
-            print(f"mp_parity {name}: world {world}, Mult rel-L2 {err[0].item():.2e}, run rel-L2 {err[1].item():.2e}, halo bytes/rhs {ev.halo_bytes()}, halo mode {ev.halo_mode()}")
+            print(f"mp_parity {name}: world {world}, Mult rel-L2 {err[0].item():.2e}, run rel-L2 {err[1].item():.2e}, halo bytes/rhs {ev.halo_bytes()}, halo mode {ev.halo_mode()}, {ev.kernel_info()[:24]}")
         worst = max(worst, float(err.max().item()))
         ev.close()
     dist.destroy_process_group()
