@@ -274,10 +274,13 @@ def main():
     barrier()
     t0 = time.perf_counter()
     te = 0.0
+    # N = 1: exactly the three calls B200RK4Solver::Step makes on a host vector in the reference's numbering
+    # (dgtd_set_state / dgtd_rk4_step / dgtd_get_state); N > 1: each rank moves its own partition (dgtd_*_state_local)
+    put, get = (ev.set_state, ev.get_state) if n_gpus == 1 else (ev.set_state_local, ev.get_state_local)
     for _ in range(e2e_steps):
-        ev.set_state_local(hx)      # host -> device (the ODESolver::Step(x, t, dt) contract: x lives on the host)
+        put(hx)                     # host -> device (the ODESolver::Step(x, t, dt) contract: x lives on the host)
         te = ev.Step(te, dt)
-        ev.get_state_local(hx)      # device -> host (synchronises)
+        get(hx)                     # device -> host (synchronises)
     barrier()
     e2e_s = time.perf_counter() - t0
     te2 = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -305,7 +308,8 @@ def main():
                              "alg_bytes_per_dof_update": B_ALG[ORDER], "alg_bytes_per_launch": alg_bytes,
                              "kernel": ev.kernel_info(), "avg_launch_ms": launch_ms},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 6 * nloc * 8 * n_gpus, "d2h_bytes_per_step": 6 * nloc * 8 * n_gpus,
-                        "steps": e2e_steps, "how": "dgtd_set_state_local(host) + dgtd_rk4_step + dgtd_get_state_local(host) per step, pinned host memory"},
+                        "steps": e2e_steps, "how": ("dgtd_set_state(host) + dgtd_rk4_step + dgtd_get_state(host) per step = B200RK4Solver::Step, pinned host memory" if n_gpus == 1 else
+                                "dgtd_set_state_local(host) + dgtd_rk4_step + dgtd_get_state_local(host) per step and rank, pinned host memory")},
                 "gpu_launches": int(launches),
                 "clocks": sampler.result()}
         if not args.no_cpu and n_gpus == 1:

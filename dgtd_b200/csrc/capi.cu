@@ -229,7 +229,7 @@ struct dgtd_ctx {
     const double *pushed = nullptr;                  // vector whose traces exchange `epoch` carries (nullptr: none valid)
     DevBuf<unsigned int> p2p_done;
     DevBuf<int> p2p_err;
-    DevBuf<int> hpush;
+    DevBuf<int> hpush, dgid;                         // dgid: local element -> caller's element index (H.elem_gid)
     long long launches = 0;
     std::vector<double> hostbuf;     // pinned staging would go here; plain vector for gather/scatter by element
     ~dgtd_ctx()
@@ -443,22 +443,24 @@ static void mult_device(dgtd_ctx *c, double t, const double *in, double *out)
     launch_stage(c, MODE_MULT, A);
 }
 
-// reference-layout device vector [6][Nloc] <-> the kernel's state layout (blocked, or aos for the warp-per-group kernel)
-static void to_device_layout(dgtd_ctx *c, const double *ref, double *dev)
+// reference-layout device vector [6][Nloc] <-> the kernel's state layout (blocked, or aos for the warp-per-group kernel);
+// gid: the vector is in the caller's element order (single rank) and the Morton permutation is applied on the fly
+static void to_device_layout(dgtd_ctx *c, const double *ref, double *dev, const int *gid = nullptr)
 {
-    if (c->wg) to_aos_kernel<<<1184, 256, 0, c->stream>>>(ref, c->Nloc, c->H.Np, c->H.NEloc, c->WP.NEpad, c->dev2ref.p, dev);
-    else to_blocked_kernel<<<1184, 256, 0, c->stream>>>(ref, c->Nloc, c->H.Np, c->H.NEloc, c->BP.NEpad, dev);
+    if (c->wg) to_aos_kernel<<<1184, 256, 0, c->stream>>>(ref, c->Nloc, c->H.Np, c->H.NEloc, c->WP.NEpad, c->dev2ref.p, gid, dev);
+    else to_blocked_kernel<<<1184, 256, 0, c->stream>>>(ref, c->Nloc, c->H.Np, c->H.NEloc, c->BP.NEpad, gid, dev);
     c->launches++;
 }
-static void from_device_layout(dgtd_ctx *c, const double *dev, double *ref)
+static void from_device_layout(dgtd_ctx *c, const double *dev, double *ref, const int *gid = nullptr)
 {
-    if (c->wg) from_aos_kernel<<<1184, 256, 0, c->stream>>>(dev, c->Nloc, c->H.Np, c->H.NEloc, c->dev2ref.p, ref);
-    else from_blocked_kernel<<<1184, 256, 0, c->stream>>>(dev, c->Nloc, c->H.Np, c->H.NEloc, ref);
+    if (c->wg) from_aos_kernel<<<1184, 256, 0, c->stream>>>(dev, c->Nloc, c->H.Np, c->H.NEloc, c->dev2ref.p, gid, ref);
+    else from_blocked_kernel<<<1184, 256, 0, c->stream>>>(dev, c->Nloc, c->H.Np, c->H.NEloc, gid, ref);
     c->launches++;
 }
 
-// local reference-layout host vector [6][Nloc] <-> device state (reference layout, or blocked through a staging buffer)
-static void upload_local(dgtd_ctx *c, const double *hloc, double *dev)
+// host vector [6][Nloc] <-> device state (reference layout, or blocked/aos through a staging buffer).  caller_order: the
+// host vector is in the caller's (global) element order of a single-rank context
+static void upload_local(dgtd_ctx *c, const double *hloc, double *dev, bool caller_order = false)
 {
     const long long Nl = c->Nloc;
     if (c->pushed == dev) c->pushed = nullptr;
@@ -467,11 +469,11 @@ static void upload_local(dgtd_ctx *c, const double *hloc, double *dev)
     } else {
         if (c->stage_ref.n != (size_t)6 * Nl) c->stage_ref.alloc((size_t)6 * Nl);
         CU(cudaMemcpyAsync(c->stage_ref.p, hloc, sizeof(double) * 6 * Nl, cudaMemcpyHostToDevice, c->stream));
-        to_device_layout(c, c->stage_ref.p, dev);
+        to_device_layout(c, c->stage_ref.p, dev, caller_order ? c->dgid.p : nullptr);
     }
     CU(cudaStreamSynchronize(c->stream));
 }
-static void download_local(dgtd_ctx *c, const double *dev, double *hloc)
+static void download_local(dgtd_ctx *c, const double *dev, double *hloc, bool caller_order = false)
 {
     const long long Nl = c->Nloc;
     p2p_check(c);
@@ -479,7 +481,7 @@ static void download_local(dgtd_ctx *c, const double *dev, double *hloc)
         CU(cudaMemcpyAsync(hloc, dev, sizeof(double) * 6 * Nl, cudaMemcpyDeviceToHost, c->stream));
     } else {
         if (c->stage_ref.n != (size_t)6 * Nl) c->stage_ref.alloc((size_t)6 * Nl);
-        from_device_layout(c, dev, c->stage_ref.p);
+        from_device_layout(c, dev, c->stage_ref.p, caller_order ? c->dgid.p : nullptr);
         CU(cudaMemcpyAsync(hloc, c->stage_ref.p, sizeof(double) * 6 * Nl, cudaMemcpyDeviceToHost, c->stream));
     }
     CU(cudaStreamSynchronize(c->stream));
@@ -489,6 +491,7 @@ static void scatter_to_device(dgtd_ctx *c, const double *host, double *dev)
 {
     const int Np = c->H.Np; const long long Ng = c->Nglob, Nl = c->Nloc;
     if (c->identity) { upload_local(c, host, dev); return; }
+    if (c->nranks == 1 && c->blocked) { upload_local(c, host, dev, true); return; }   // the permutation runs on the device
     c->hostbuf.resize((size_t)6 * Nl);
     for (int comp = 0; comp < 6; comp++)
         for (int le = 0; le < c->H.NEloc; le++)
@@ -499,6 +502,7 @@ static void gather_from_device(dgtd_ctx *c, const double *dev, double *host)
 {
     const int Np = c->H.Np; const long long Ng = c->Nglob, Nl = c->Nloc;
     if (c->identity) { download_local(c, dev, host); return; }
+    if (c->nranks == 1 && c->blocked) { download_local(c, dev, host, true); return; }
     c->hostbuf.resize((size_t)6 * Nl);
     download_local(c, dev, c->hostbuf.data());
     for (int comp = 0; comp < 6; comp++)
@@ -692,6 +696,7 @@ int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
     c->tfsf_xyz.upload(H.tfsf_xyz, 3); c->gate_xyz.upload(H.gate_xyz, 3); c->gate.alloc(4);
     CU(cudaMemset(c->gate.p, 0, 4 * sizeof(double)));
     c->send_node.upload(H.send_node, 1);
+    c->dgid.upload(H.elem_gid, 1);
     const size_t hn = std::max<size_t>(1, (size_t)6 * H.n_halo_faces * H.Nfp);
     c->halo.alloc(hn); c->sendbuf.alloc(hn); c->scratch.alloc(4);
     CU(cudaMemset(c->halo.p, 0, hn * sizeof(double)));

@@ -410,22 +410,25 @@ __global__ void __launch_bounds__(Blk<P, G>::T, G == 1 ? 2 : 1) stage_mma_kernel
 }
 
 // ---- layout conversion between the reference layout [6][Nloc] (Fields.h:45-65) and the blocked device layout ----------
-__global__ void to_blocked_kernel(const double *ref, long long stride, int Np, long long NEloc, long long NEpad, double *blk)
+// gid != nullptr: `ref` is in the caller's element order, local element e is element gid[e] there
+__global__ void to_blocked_kernel(const double *ref, long long stride, int Np, long long NEloc, long long NEpad, const int *gid, double *blk)
 {
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < NEpad * Np; idx += (long long)gridDim.x * blockDim.x) {
         const long long e = idx / Np; const int j = (int)(idx - e * Np);
         double *o = blk + (((e >> 3) * Np + j) * BLK_E + (e & 7)) * 6;
+        const long long src = (gid && e < NEloc ? (long long)gid[e] : e) * Np + j;
 #pragma unroll
-        for (int c = 0; c < 6; c++) o[c] = e < NEloc ? ref[c * stride + idx] : 0.0;
+        for (int c = 0; c < 6; c++) o[c] = e < NEloc ? ref[c * stride + src] : 0.0;
     }
 }
-__global__ void from_blocked_kernel(const double *blk, long long stride, int Np, long long NEloc, double *ref)
+__global__ void from_blocked_kernel(const double *blk, long long stride, int Np, long long NEloc, const int *gid, double *ref)
 {
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < NEloc * Np; idx += (long long)gridDim.x * blockDim.x) {
         const long long e = idx / Np; const int j = (int)(idx - e * Np);
         const double *o = blk + (((e >> 3) * Np + j) * BLK_E + (e & 7)) * 6;
+        const long long dst = (gid ? (long long)gid[e] : e) * Np + j;
 #pragma unroll
-        for (int c = 0; c < 6; c++) ref[c * stride + idx] = o[c];
+        for (int c = 0; c < 6; c++) ref[c * stride + dst] = o[c];
     }
 }
 // halo pack: send[s][c] = y[send_off[s] + c]  (48-byte node records, receiver's face-node order)

@@ -445,22 +445,24 @@ __global__ void halo_push_kernel(const double *y, const long long *send_off, int
 }
 
 // ---- layout conversion between the reference layout [6][Nloc] (Fields.h:45-65) and the aos device layout ---------------
-__global__ void to_aos_kernel(const double *ref, long long stride, int Np, long long NEloc, long long NEpad, const int *dev2ref, double *aos)
+// gid != nullptr: `ref` is in the caller's element order and local element e is element gid[e] there (single rank: the
+// Morton permutation is applied here instead of in a host loop)
+__global__ void to_aos_kernel(const double *ref, long long stride, int Np, long long NEloc, long long NEpad, const int *dev2ref, const int *gid, double *aos)
 {
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < NEpad * Np; idx += (long long)gridDim.x * blockDim.x) {
         const long long e = idx / Np; const int n = (int)(idx - e * Np);
         double *o = aos + idx * 6;
-        const long long src = e * Np + dev2ref[n];
+        const long long src = (gid && e < NEloc ? (long long)gid[e] : e) * Np + dev2ref[n];
 #pragma unroll
         for (int c = 0; c < 6; c++) o[c] = e < NEloc ? ref[c * stride + src] : 0.0;
     }
 }
-__global__ void from_aos_kernel(const double *aos, long long stride, int Np, long long NEloc, const int *dev2ref, double *ref)
+__global__ void from_aos_kernel(const double *aos, long long stride, int Np, long long NEloc, const int *dev2ref, const int *gid, double *ref)
 {
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < NEloc * Np; idx += (long long)gridDim.x * blockDim.x) {
         const long long e = idx / Np; const int n = (int)(idx - e * Np);
         const double *o = aos + idx * 6;
-        const long long dst = e * Np + dev2ref[n];
+        const long long dst = (gid ? (long long)gid[e] : e) * Np + dev2ref[n];
 #pragma unroll
         for (int c = 0; c < 6; c++) ref[c * stride + dst] = o[c];
     }
