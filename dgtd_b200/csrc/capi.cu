@@ -1078,6 +1078,7 @@ int dgtd_comm_init(dgtd_ctx *c, const void *id128)
     GUARD_BEGIN
     if (!c || !id128) throw Error(DGTD_ERR_ARG, "null argument");
     if (c->nranks == 1) return DGTD_OK;
+    if (c->comm) throw Error(DGTD_ERR_COMM, "dgtd_comm_init: this context already has a communicator");
     CU(cudaSetDevice(c->device));
     g_nccl.load();
     NcclId id; std::memcpy(&id, id128, 128);

@@ -174,7 +174,10 @@ int  dgtd_kernel_info(const dgtd_ctx *, char *buf, int cap);
  * buffers with CUDA IPC; from then on the stage kernel itself stores the traces of its partition faces into the
  * neighbour's buffer and only the warps owning such a face wait for the neighbour's epoch flag (no pack kernel, no
  * collective on the path).  If IPC is unavailable on any rank, all ranks use ncclSend/ncclRecv instead.
- * dgtd_destroy of a multi-rank context is collective too (neighbours must stop storing before a buffer is freed).   */
+ * dgtd_destroy of a multi-rank context is collective too (neighbours must stop storing before a buffer is freed).
+ * Like the reference's MPI calls, every entry point that evaluates the operator or replaces the state (dgtd_mult,
+ * dgtd_rk4_step/run/run_until, dgtd_set_state*) must be called by ALL ranks in the same order: each one is one numbered
+ * exchange of the neighbours' traces.                                                                                */
 int  dgtd_comm_unique_id(void *id128);                    /* rank 0: ncclGetUniqueId              */
 int  dgtd_comm_init(dgtd_ctx *, const void *id128);       /* all ranks                            */
 #define DGTD_HALO_NONE 0   /* single rank                                         */
