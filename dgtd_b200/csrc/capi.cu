@@ -10,7 +10,7 @@
 #include "kernels_mma.cuh"
 #include "kernels_ws.cuh"
 #include "kernels_wg.cuh"
-#include "kernels_wp.cuh"
+#include "kernels_wh.cuh"
 
 #include <dlfcn.h>
 #include <cmath>
@@ -169,20 +169,20 @@ static bool select_wg(int dim, int p, bool tf, WgSet &ws)
     return false;
 }
 
-// the warp-pair kernel (kernels_wp.cuh): same plan and layout as the warp-per-group kernel, two warps per group
-template <int P, bool TF> static WgSet wpset()
+// the half-row kernel (kernels_wh.cuh): same plan and layout, one warp per group of FOUR elements, rows = (element, field)
+template <int P, bool TF> static WgSet whset()
 {
-    using B = Wp<P>;
-    return {{stage_wp_kernel<P, 0, TF>, stage_wp_kernel<P, 1, TF>, stage_wp_kernel<P, 2, TF>, stage_wp_kernel<P, 3, TF>}, B::T, B::smem_bytes};
+    using B = Wh<P>;
+    return {{stage_wh_kernel<P, 0, TF>, stage_wh_kernel<P, 1, TF>, stage_wh_kernel<P, 2, TF>, stage_wh_kernel<P, 3, TF>}, B::T, B::smem_bytes};
 }
-static bool select_wp(int dim, int p, bool tf, WgSet &ws, int &groups_per_cta)
+static bool select_wh(int dim, int p, bool tf, WgSet &ws, int &groups_per_cta)
 {
     if (dim != 3) return false;
     switch (p) {
-        case 1: ws = tf ? wpset<1, true>() : wpset<1, false>(); groups_per_cta = Wp<1>::NG; return true;
-        case 2: ws = tf ? wpset<2, true>() : wpset<2, false>(); groups_per_cta = Wp<2>::NG; return true;
-        case 3: ws = tf ? wpset<3, true>() : wpset<3, false>(); groups_per_cta = Wp<3>::NG; return true;
-        case 4: ws = tf ? wpset<4, true>() : wpset<4, false>(); groups_per_cta = Wp<4>::NG; return true;
+        case 1: ws = tf ? whset<1, true>() : whset<1, false>(); groups_per_cta = Wh<1>::NW; return true;
+        case 2: ws = tf ? whset<2, true>() : whset<2, false>(); groups_per_cta = Wh<2>::NW; return true;
+        case 3: ws = tf ? whset<3, true>() : whset<3, false>(); groups_per_cta = Wh<3>::NW; return true;
+        case 4: ws = tf ? whset<4, true>() : whset<4, false>(); groups_per_cta = Wh<4>::NW; return true;
     }
     return false;
 }
@@ -192,7 +192,7 @@ struct dgtd_ctx {
     BlockedPlan BP;
     WgPlan WP;
     bool has_sigma = false;
-    bool wp = false;                 // ... or its warp-pair form (kernels_wp.cuh); wg stays set: same plan and layout
+    bool wh = false;                 // ... or its half-row form (kernels_wh.cuh, groups of 4 elements); wg stays set: same plan and layout
     int wg_groups_per_cta = 0;
     bool wg = false;                 // aos layout + warp-per-group kernel (blocked is set too: state needs layout conversion)
     WgSet wgs{};
@@ -642,11 +642,13 @@ int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
     const bool has_tf = H.pw.enabled && H.n_tfsf_faces > 0;
     // default: the warp-pair kernel at order 4 (8 instead of 4 warps per SM: 69 vs 60 G DOF-updates/s), the one-warp kernel
     // below it (at order 3 the pair's doubled fragment / trace loads make it shared-memory bound: 82 vs 110 G)
-    if ((ksel == "wp" || (ksel.empty() && H.p == 4)) && select_wp(H.dim, H.p, has_tf, c->wgs, c->wg_groups_per_cta) && c->wgs.smem <= (size_t)prop.sharedMemPerBlockOptin) {
+    // default: the half-row kernel at order 4 (8 instead of 4 warps per SM: 77 vs 60 G DOF-updates/s), the one-warp-per-8
+    // kernel below it (order 3: 109 vs 107 G, order 2: 102 vs 91 G)
+    if ((ksel == "wh" || (ksel.empty() && H.p == 4)) && select_wh(H.dim, H.p, has_tf, c->wgs, c->wg_groups_per_cta) && c->wgs.smem <= (size_t)prop.sharedMemPerBlockOptin) {
         c->WP = build_wg_plan(H);
-        if (c->WP.ntab <= Wg<3>::TABROWS) c->blocked = c->wg = c->wp = true;
+        if (c->WP.ntab <= Wg<3>::TABROWS) c->blocked = c->wg = c->wh = true;
     }
-    if (!c->wg && (ksel == "wg" || ksel == "wp" || ksel.empty()) && select_wg(H.dim, H.p, has_tf, c->wgs) && c->wgs.smem <= (size_t)prop.sharedMemPerBlockOptin) {
+    if (!c->wg && (ksel == "wg" || ksel == "wh" || ksel.empty()) && select_wg(H.dim, H.p, has_tf, c->wgs) && c->wgs.smem <= (size_t)prop.sharedMemPerBlockOptin) {
         c->WP = build_wg_plan(H);
         c->wg_groups_per_cta = c->wgs.threads / 32;
         if (c->WP.ntab <= Wg<3>::TABROWS) c->blocked = c->wg = true;
@@ -655,7 +657,8 @@ int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
         c->Nalloc = (long long)c->WP.NEpad * H.Np;
         for (int m = 0; m < 4; m++) CU(cudaFuncSetAttribute((const void *)c->wgs.fn[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->wgs.smem));
         const int nw = c->wg_groups_per_cta;
-        c->grid = (int)std::min<long long>(((long long)c->WP.ngroups + nw - 1) / nw, (long long)prop.multiProcessorCount);
+        const long long units = (long long)c->WP.ngroups * (c->wh ? BLK_E / WH_E : 1);      // groups of 8, or of 4 elements
+        c->grid = (int)std::min<long long>((units + nw - 1) / nw, (long long)prop.multiProcessorCount);
         c->bgeo.upload(c->WP.geo); c->bafrag.upload(c->WP.bfrag); c->bdesc.upload(c->WP.desc); c->bsend_off.upload(c->WP.send_off, 1);
         c->wtab.upload(c->WP.tab, 16); c->dev2ref.upload(c->WP.dev2ref); c->hpush.upload(c->WP.hpush, 2);
     } else if (ksel != "generic" && tabs_ok) {
@@ -996,8 +999,8 @@ int dgtd_kernel_info(const dgtd_ctx *c, char *buf, int cap)
 {
     if (!c || !buf || cap < 1) return fail(DGTD_ERR_ARG, "bad argument");
     char tmp[320];
-    if (c->wp)
-        std::snprintf(tmp, sizeof tmp, "stage_wp_kernel<P=%d,MODE> DMMA m8n8k4 transposed, warp pair (E rows / H rows) per group of 8 elements, aos layout, %d threads, %zu B smem, grid %d%s",
+    if (c->wh)
+        std::snprintf(tmp, sizeof tmp, "stage_wh_kernel<P=%d,MODE> DMMA m8n8k4 transposed, warp per group of 4 elements (rows = element x field), aos layout, %d threads, %zu B smem, grid %d%s",
                       c->H.p, c->wgs.threads, c->wgs.smem, c->grid, c->nranks == 1 ? "" : c->p2p ? ", halo: fused peer-memory stores" : ", halo: NCCL send/recv");
     else if (c->wg)
         std::snprintf(tmp, sizeof tmp, "stage_wg_kernel<P=%d,MODE> DMMA m8n8k4 transposed, warp per group of 8 elements, aos layout, %d threads, %zu B smem, grid %d%s",

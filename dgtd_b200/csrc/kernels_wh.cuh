@@ -1,17 +1,19 @@
-// sm_100a warp-PAIR DMMA stage kernel (tetrahedra): the warp-per-group kernel of kernels_wg.cuh with each group of 8
-// elements carried by TWO warps that share the group's shared-memory buffers — warp role h = 0 forms the E rows of the
-// stage (k_E from u~_H and the E flux), h = 1 the H rows.
+// sm_100a "half-row" DMMA stage kernel (tetrahedra): one warp carries a group of FOUR elements; the eight DMMA rows are
+// (element, field): row r = 2 e + h feeds / accumulates the E rows (h = 0) or the H rows (h = 1) of element e.
 //
-// Why (profiles/r1_final_stage_wg_ncu_summary.txt, tools: DGTD_WG_NW sweep): the one-warp kernel keeps 72 accumulator registers
-// and 25 KB of buffers per warp, so 8 warps fill an SM (2 per scheduler) and the FP64 pipe idles 28 % of the time on
-// latencies nobody covers (4 -> 8 warps per SM bought +35 %).  Halving the accumulator set per warp (36 registers at order
-// 3) lets 12 warps (3 per scheduler, 6 groups in flight) fit the register file at order 3, and 8 instead of 4 warps at
-// order 4, for ~12 % more FP64 ALU work (both warps form the jumps).
-//   * same state layout ("aos"), plan (WgPlan), operator fragments, TMA staging and peer-memory halo as kernels_wg.cuh;
-//   * role-dependent data is reached through pointer offsets (own = 3h, other = 3 - 3h doubles into a node record) and
-//     sign-folded operators, never through run-time register indexing;
-//   * the two warps of a pair meet at two named barriers per group: after the last read of y_in (the next group's y_in
-//     may land) and after the epilogue (the bulk stores and the halo push read complete records).
+// Why: the one-warp-per-8-elements kernel (kernels_wg.cuh) needs 72 accumulator registers and 25 KB of buffers per warp,
+// so 8 warps fill an SM at order 3 and only 4 at order 4.  Splitting a group between two WARPS by field (tried: 12 warps at
+// order 3, 8 at order 4) halves the accumulators but doubles the operator-fragment and trace loads and needs two named
+// barriers per group: 82 G at order 3 (shared-memory bound), 69 G at order 4.  Here the same field split happens between
+// the ROWS of one DMMA: a fragment load still serves eight rows, the two lanes that need the same node record read the same
+// address (one broadcast), the accumulator set is 36 registers, a warp's buffers are 12.7 KB — 12 warps per SM at order
+// <= 3 (3 per scheduler), 8 at order 4, no barrier between warps.  Cost: both rows of an element form the jumps
+// (+25 % of the flux's FP64 ALU work, +3 % of the pipe time).
+//   lane l: DMMA row r = l >> 2 -> element e = r >> 1 of the group, field h = r & 1; j = l & 3 is the k index (node of a
+//   k-step in the volume contraction, face in the flux) exactly as in kernels_wg.cuh; own = 3h / other = 3 - 3h are the
+//   offsets of "my" and "the other" field inside a 6-double node record.
+// State layout, plan (WgPlan: per-element geometry and descriptors, fragments, tables, halo push) and the peer-memory
+// halo are those of kernels_wg.cuh; a group is simply half of one of its groups.
 // Reference semantics: src/evolution/HesthavenEvolution.cpp:450-542 with the `global` operator's coefficients
 // (src/components/DGOperatorFactory.h:469-573, 1268-1361), external/mfem-geg/linalg/ode.cpp:109-136.
 #pragma once
@@ -19,34 +21,33 @@
 
 namespace dgtd {
 
-#ifndef DGTD_WP_NG
-#define DGTD_WP_NG 6
+constexpr int WH_E = 4;                // elements per group
+__device__ __forceinline__ void load3(const double *p, double *u) { u[0] = p[0]; u[1] = p[1]; u[2] = p[2]; }
+__device__ __forceinline__ void store3(double *p, const double *u) { p[0] = u[0]; p[1] = u[1]; p[2] = u[2]; }
+#ifndef DGTD_WH_NW
+#define DGTD_WH_NW 12
 #endif
-template <int P> struct Wp {
+template <int P> struct Wh {
     static constexpr int Np = (P + 1) * (P + 2) * (P + 3) / 6, Nfp = (P + 1) * (P + 2) / 2;
     static constexpr int NT = (Np + 7) / 8, KSV = (Np + 3) / 4, VT = (NT - 1) * 3 + 3;
-    static constexpr int NG = P <= 3 ? DGTD_WP_NG : 4, NW = 2 * NG, T = 32 * NW;   // groups in flight per SM, warps
-    static constexpr int GS = Np * BLK_E * 6;
+    static constexpr int NW = P <= 3 ? DGTD_WH_NW : 8, T = 32 * NW;             // warps per CTA = groups in flight per SM
+    static constexpr int GS = Np * WH_E * 6;                                    // doubles per group of one state vector
     static constexpr int NFV = KSV * VT, NFL = Nfp * NT, NFR = NFV + NFL;
-    static constexpr int WGEO = BLK_E * BLK_GEO, WDESC = BLK_E * 4 * 2;
+    static constexpr int WGEO = WH_E * BLK_GEO, WDESC = WH_E * 4 * 2;
     static constexpr int WDBL = 3 * GS + WGEO + WDESC / 2;
     static constexpr int TABROWS = 136;
     static constexpr int oWarp = NFR * 32;
-    static constexpr size_t bTab = (size_t)(oWarp + NG * WDBL) * 8;
+    static constexpr size_t bTab = (size_t)(oWarp + NW * WDBL) * 8;
     static constexpr size_t bBar = bTab + (size_t)TABROWS * 16;
-    static constexpr size_t smem_bytes = bBar + (size_t)NG * 2 * 8;
+    static constexpr size_t smem_bytes = bBar + (size_t)NW * 2 * 8;
     static_assert(Np - 8 * (NT - 1) <= 4, "mixed last tile");
-    static_assert((GS % 2) == 0 && (bTab % 16) == 0, "alignment");
+    static_assert((GS % 2) == 0 && (bTab % 16) == 0 && (WDBL % 2) == 0, "alignment");
 };
 
-__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void load3(const double *p, double *u) { u[0] = p[0]; u[1] = p[1]; u[2] = p[2]; }
-__device__ __forceinline__ void store3(double *p, const double *u) { p[0] = u[0]; p[1] = u[1]; p[2] = u[2]; }
-
 template <int P, int MODE, bool TF>
-__global__ void __launch_bounds__(Wp<P>::T, 1) stage_wp_kernel(const WgArgs A)
+__global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
 {
-    using B = Wp<P>;
+    using B = Wh<P>;
     constexpr int Np = B::Np, Nfp = B::Nfp, NT = B::NT, KSV = B::KSV, VT = B::VT, GS = B::GS;
     constexpr int NL = Np - 8 * (NT - 1);
     constexpr int PF = 1;
@@ -58,13 +59,13 @@ __global__ void __launch_bounds__(Wp<P>::T, 1) stage_wp_kernel(const WgArgs A)
     const double *sFragV = sm, *sFragL = sm + B::NFV * 32;
     const uint4 *sTab = reinterpret_cast<const uint4 *>(smem_wg + B::bTab);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, e = lane >> 2, j = lane & 3;
-    const int h = warp & 1, gs = warp >> 1;              // role (0: E rows, 1: H rows), group slot
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, j = lane & 3;
+    const int e = lane >> 3, h = (lane >> 2) & 1;        // element of the group, field of my DMMA row (0: E rows, 1: H rows)
     const int own = 3 * h, oth = 3 - own;                // doubles into a node record: my output field / the other one
-    const bool leader = h == 0 && lane == 0;
-    double *wY = sm + B::oWarp + gs * B::WDBL, *wX = wY + GS, *wZ = wX + GS, *wGeo = wZ + GS;
+    const bool leader = lane == 0;
+    double *wY = sm + B::oWarp + warp * B::WDBL, *wX = wY + GS, *wZ = wX + GS, *wGeo = wZ + GS;
     const int2 *wDesc = reinterpret_cast<const int2 *>(wGeo + B::WGEO);
-    uint64_t *barY = reinterpret_cast<uint64_t *>(smem_wg + B::bBar) + 2 * gs, *barXZ = barY + 1;
+    uint64_t *barY = reinterpret_cast<uint64_t *>(smem_wg + B::bBar) + 2 * warp, *barXZ = barY + 1;
 
     for (int i = tid; i < B::NFR * 32; i += B::T) sm[i] = A.bfrag[i];
     {
@@ -77,8 +78,8 @@ __global__ void __launch_bounds__(Wp<P>::T, 1) stage_wp_kernel(const WgArgs A)
     fence_async_smem();
     __syncthreads();
 
-    const int gstride = gridDim.x * B::NG;
-    int g = blockIdx.x * B::NG + gs;
+    const int gstride = gridDim.x * B::NW, ngroups = A.ngroups * (BLK_E / WH_E);   // WgArgs counts groups of 8
+    int g = blockIdx.x * B::NW + warp;
     bool halo_ready = A.pp.wait_epoch == 0;
     const uint4 ownrow = sTab[j];
     const bool inject = A.pw_on && (A.gate == nullptr || *A.gate >= 1e-16);
@@ -95,9 +96,9 @@ __global__ void __launch_bounds__(Wp<P>::T, 1) stage_wp_kernel(const WgArgs A)
         if (LOAD_X) bulk_load(wX, (MODE == MODE_STAGE1 ? A.yin : A.x) + (size_t)gg * GS, GS * 8, barXZ);
         if (LOAD_Z) bulk_load(wZ, A.z + (size_t)gg * GS, GS * 8, barXZ);
     };
-    if (leader && g < A.ngroups) { issue_y(g); if (LOAD_X || LOAD_Z) issue_xz(g); }
+    if (leader && g < ngroups) { issue_y(g); if (LOAD_X || LOAD_Z) issue_xz(g); }
 
-    for (int it = 0; g < A.ngroups; g += gstride, it++) {
+    for (int it = 0; g < ngroups; g += gstride, it++) {
         const uint32_t par = it & 1;
         const double *ge = wGeo + e * BLK_GEO;
         const double *yrec = wY + e * Np * 6;
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(Wp<P>::T, 1) stage_wp_kernel(const WgArgs A)
         double ce = 0.0, ch = 0.0, al = A.alpha;
         if (info.x >= 0) {
             nrow = sTab[(code >> FI_TAB_SHIFT) & FI_TAB_MASK];
-            nbase = (info.x >> 3) == g ? wY + (info.x & 7) * Np * 6 : A.yin + (size_t)info.x * Np * 6;
+            nbase = (info.x >> 2) == g ? wY + (info.x & 3) * Np * 6 : A.yin + (size_t)info.x * Np * 6;
         } else if (info.x == -1) {
             const int bc = code & FI_BC_MASK;
             ce = bc == 1 ? -2.0 : bc == 3 ? -1.0 : 0.0;
@@ -241,8 +242,8 @@ __global__ void __launch_bounds__(Wp<P>::T, 1) stage_wp_kernel(const WgArgs A)
         const bool keep_y = A.has_sigma != 0;
         const int gnext = g + gstride;
         if (!keep_y) {
-            pair_sync(1 + gs);                              // both warps have read y_in for the last time
-            if (leader && gnext < A.ngroups) issue_y(gnext);
+            __syncwarp();                                   // every lane has read y_in for the last time
+            if (leader && gnext < ngroups) issue_y(gnext);
         }
         if (LOAD_X || LOAD_Z) mbar_wait(barXZ, par);
         const bool plain = keep_y || MODE == MODE_MULT;
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(Wp<P>::T, 1) stage_wp_kernel(const WgArgs A)
                 if (STORE_Z) store3(wZ + off, zn);
             }
         fence_async_smem();
-        pair_sync(1 + gs);                                  // complete records in wX / wZ
+        __syncwarp();                                       // complete records in wX / wZ
         if (h == 0) {
             if (MODE != MODE_MULT && A.pp.signal_epoch != 0 && info.x < -1) {
                 const int2 hp = A.pp.hpush[-2 - info.x];
@@ -306,11 +307,11 @@ __global__ void __launch_bounds__(Wp<P>::T, 1) stage_wp_kernel(const WgArgs A)
                 if (MODE == MODE_STAGE4) bulk_store(A.yout + goff, wZ, GS * 8);
                 else if (STORE_Z) bulk_store(A.z + goff, wZ, GS * 8);
                 bulk_commit();
-                if (keep_y && gnext < A.ngroups) issue_y(gnext);
+                if (keep_y && gnext < ngroups) issue_y(gnext);
                 if (!(LOAD_X || LOAD_Z)) bulk_wait_read();
             }
         }
-        if (!(LOAD_X || LOAD_Z)) pair_sync(1 + gs);         // Mult: the partner must not overwrite wX before the store has read it
+        __syncwarp();
     }
     if (leader) bulk_wait_all();
     if (MODE != MODE_MULT && A.pp.signal_epoch != 0) p2p_signal(A.pp);
