@@ -134,6 +134,19 @@ __device__ __forceinline__ void load_rec(const double *p, double *u)
     const double2 a = q[0], b = q[1], c = q[2];
     u[0] = a.x; u[1] = a.y; u[2] = b.x; u[3] = b.y; u[4] = c.x; u[5] = c.y;
 }
+// neighbour record whose address space is known per lane: a generic LD whose lanes fall partly into shared memory costs
+// ~8.5 shared-memory wavefronts per instruction against 2 for the same lanes through LDS (profiles/r1_final_stage_wg_ncu_summary.txt)
+__device__ __forceinline__ void load_rec_split(const double *p, bool in_smem, double *u)
+{
+    if (in_smem) {
+        const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%6];\n\tld.shared.v2.f64 {%2,%3}, [%6+16];\n\tld.shared.v2.f64 {%4,%5}, [%6+32];"
+                     : "=d"(u[0]), "=d"(u[1]), "=d"(u[2]), "=d"(u[3]), "=d"(u[4]), "=d"(u[5]) : "r"(a));
+    } else {
+        asm volatile("ld.global.v2.f64 {%0,%1}, [%6];\n\tld.global.v2.f64 {%2,%3}, [%6+16];\n\tld.global.v2.f64 {%4,%5}, [%6+32];"
+                     : "=d"(u[0]), "=d"(u[1]), "=d"(u[2]), "=d"(u[3]), "=d"(u[4]), "=d"(u[5]) : "l"(p));
+    }
+}
 __device__ __forceinline__ void store_rec(double *p, const double *u)
 {
     double2 *q = reinterpret_cast<double2 *>(p);
@@ -217,9 +230,11 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
         const double *nbase = yrec;
         uint4 nrow = ownrow;
         double ce = 0.0, ch = 0.0, al = A.alpha;
+        bool nb_smem = true;                                  // the exterior trace lies in this warp's own y_in buffer
         if (info.x >= 0) {
             nrow = sTab[(code >> FI_TAB_SHIFT) & FI_TAB_MASK];
-            nbase = (info.x >> 3) == g ? wY + (info.x & 7) * Np * 6 : A.yin + (size_t)info.x * Np * 6;
+            nb_smem = (info.x >> 3) == g;
+            nbase = nb_smem ? wY + (info.x & 7) * Np * 6 : A.yin + (size_t)info.x * Np * 6;
         } else if (info.x == -1) {
             const int bc = code & FI_BC_MASK;
             ce = bc == 1 ? -2.0 : bc == 3 ? -1.0 : 0.0;
@@ -227,12 +242,13 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
             if (bc == 3) al = 1.0;
         } else {
             nrow = sTab[4 + j];
+            nb_smem = false;
             nbase = A.halo + (size_t)(-2 - info.x) * Nfp * 6;
         }
         if (!halo_ready && __any_sync(0xffffffffu, info.x < -1)) { p2p_wait(A.pp, lane); halo_ready = true; }
         double uQ[PF + 1][6];
 #pragma unroll
-        for (int q = 0; q < PF; q++) load_rec(nbase + tab_byte(nrow, q) * 6, uQ[q]);
+        for (int q = 0; q < PF; q++) load_rec_split(nbase + tab_byte(nrow, q) * 6, nb_smem, uQ[q]);
 
         // ---------------- volume: k~E_c = D_{c+1} u~H_{c+2} - D_{c+2} u~H_{c+1},  k~H likewise from u~E = -J^T E / det ------
         {
@@ -304,7 +320,7 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
                 double uM[6], dU[6];
                 const double *uP = uQ[s % (PF + 1)];
                 load_rec(yrec + tab_byte(ownrow, s) * 6, uM);
-                if (s + PF < Nfp) load_rec(nbase + tab_byte(nrow, s + PF) * 6, uQ[(s + PF) % (PF + 1)]);
+                if (s + PF < Nfp) load_rec_split(nbase + tab_byte(nrow, s + PF) * 6, nb_smem, uQ[(s + PF) % (PF + 1)]);
 #pragma unroll
                 for (int c = 0; c < 3; c++) { dU[c] = fma(-se1, uM[c], uP[c]); dU[3 + c] = fma(-sh1, uM[3 + c], uP[3 + c]); }   // u+ - u- (+ c u-)
                 if (TF && tf && inject) {

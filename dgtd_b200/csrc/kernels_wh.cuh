@@ -116,9 +116,11 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
         const double *nbase = yrec;
         uint4 nrow = ownrow;
         double ce = 0.0, ch = 0.0, al = A.alpha;
+        bool nb_smem = true;                                  // the exterior trace lies in this warp's own y_in buffer
         if (info.x >= 0) {
             nrow = sTab[(code >> FI_TAB_SHIFT) & FI_TAB_MASK];
-            nbase = (info.x >> 2) == g ? wY + (info.x & 3) * Np * 6 : A.yin + (size_t)info.x * Np * 6;
+            nb_smem = (info.x >> 2) == g;
+            nbase = nb_smem ? wY + (info.x & 3) * Np * 6 : A.yin + (size_t)info.x * Np * 6;
         } else if (info.x == -1) {
             const int bc = code & FI_BC_MASK;
             ce = bc == 1 ? -2.0 : bc == 3 ? -1.0 : 0.0;
@@ -126,12 +128,13 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
             if (bc == 3) al = 1.0;
         } else {
             nrow = sTab[4 + j];
+            nb_smem = false;
             nbase = A.halo + (size_t)(-2 - info.x) * Nfp * 6;
         }
         if (!halo_ready && __any_sync(0xffffffffu, info.x < -1)) { p2p_wait(A.pp, lane); halo_ready = true; }
         double uQ[PF + 1][6];
 #pragma unroll
-        for (int q = 0; q < PF; q++) load_rec(nbase + tab_byte(nrow, q) * 6, uQ[q]);
+        for (int q = 0; q < PF; q++) load_rec_split(nbase + tab_byte(nrow, q) * 6, nb_smem, uQ[q]);
 
         // ---------------- volume: my field's k~_c = D_{c+1} u~_{c+2} - D_{c+2} u~_{c+1} of the OTHER field ---------------------
         {
@@ -198,7 +201,7 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
                 double mO[3], mX[3], dO[3], dX[3];
                 load3(mrec + own, mO);
                 load3(mrec + oth, mX);
-                if (s + PF < Nfp) load_rec(nbase + tab_byte(nrow, s + PF) * 6, uQ[(s + PF) % (PF + 1)]);
+                if (s + PF < Nfp) load_rec_split(nbase + tab_byte(nrow, s + PF) * 6, nb_smem, uQ[(s + PF) % (PF + 1)]);
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
                     const double pO = h ? uP[3 + c] : uP[c], pX = h ? uP[c] : uP[3 + c];
