@@ -133,13 +133,17 @@ inline long long blocked_offset(int Np, long long le, int node) { return (((le >
 // id (dev2ref maps it to the reference node); 8 consecutive local elements form a group = one warp's unit of work, one
 // contiguous chunk of Np*8*6 doubles.  The contraction runs "transposed" (DMMA A = data [8 elements x 4 nodes],
 // B = operator [4 nodes x 8 output nodes]) so that a lane owns one element through all phases.
+// geometry record stride of the wg / wh kernels: the 26 doubles of BLK_GEO's record padded to 34, so that the records of the
+// 8 elements of a group start 4 banks apart in shared memory (a stride of 32 doubles puts them all on the same banks: every
+// geometry LDS.128 cost 8 wavefronts instead of 1)
+constexpr int WG_GEO = 34;
 struct WgPlan {
     int ngroups = 0, NEpad = 0;
     int NT = 0, KSV = 0;               // output n-tiles (the last one is "mixed"), k-steps of the volume contraction
     int nfrag_vol = 0, nfrag_lift = 0; // B fragments of 32 doubles: volume [KSV][(NT-1)*3 + 3], LIFT [Nfp][NT]
     std::vector<int> dev2ref, ref2dev; // Np
     std::vector<int> forder;           // 4*Nfp : step s of face f handles canonical face node forder[f*Nfp+s]
-    std::vector<double> geo;           // NEpad * BLK_GEO
+    std::vector<double> geo;           // NEpad * WG_GEO
     std::vector<int> desc;             // NEpad*4*2 : {nbr local element | -1 boundary | -2-haloFace, code (FI_TAB = row of tab)}
     std::vector<uint8_t> tab;          // ntab*16 : rows 0..3 own device node per step, 4..7 canonical index per step, 8.. neighbour device node per step
     int ntab = 0;

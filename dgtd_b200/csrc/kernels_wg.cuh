@@ -111,7 +111,7 @@ template <int P> struct Wg {
     static constexpr int NW = P <= 3 ? DGTD_WG_NW : 4, T = 32 * NW;       // warps per CTA = groups in flight per SM
     static constexpr int GS = Np * BLK_E * 6;                    // doubles per group of one state vector
     static constexpr int NFV = KSV * VT, NFL = Nfp * NT, NFR = NFV + NFL;
-    static constexpr int WGEO = BLK_E * BLK_GEO, WDESC = BLK_E * 4 * 2;   // doubles / ints per group
+    static constexpr int WGEO = BLK_E * WG_GEO, WDESC = BLK_E * 4 * 2;   // doubles / ints per group
     static constexpr int WDBL = 3 * GS + WGEO + WDESC / 2;       // doubles per warp: Y, X, Z, geometry, descriptors
     static constexpr int TABROWS = 136;
     static constexpr int oWarp = NFR * 32;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
 
     for (int it = 0; g < A.ngroups; g += gstride, it++) {
         const uint32_t par = it & 1;
-        const double *ge = wGeo + e * BLK_GEO;
+        const double *ge = wGeo + e * WG_GEO;
         const double *yrec = wY + e * Np * 6;
         mbar_wait(barY, par);
 

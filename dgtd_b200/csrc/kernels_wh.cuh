@@ -33,7 +33,7 @@ template <int P> struct Wh {
     static constexpr int NW = P <= 3 ? DGTD_WH_NW : 8, T = 32 * NW;             // warps per CTA = groups in flight per SM
     static constexpr int GS = Np * WH_E * 6;                                    // doubles per group of one state vector
     static constexpr int NFV = KSV * VT, NFL = Nfp * NT, NFR = NFV + NFL;
-    static constexpr int WGEO = WH_E * BLK_GEO, WDESC = WH_E * 4 * 2;
+    static constexpr int WGEO = WH_E * WG_GEO, WDESC = WH_E * 4 * 2;
     static constexpr int WDBL = 3 * GS + WGEO + WDESC / 2;
     static constexpr int TABROWS = 136;
     static constexpr int oWarp = NFR * 32;
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
 
     for (int it = 0; g < ngroups; g += gstride, it++) {
         const uint32_t par = it & 1;
-        const double *ge = wGeo + e * BLK_GEO;
+        const double *ge = wGeo + e * WG_GEO;
         const double *yrec = wY + e * Np * 6;
         mbar_wait(barY, par);
 

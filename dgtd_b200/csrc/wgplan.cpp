@@ -31,9 +31,9 @@ WgPlan build_wg_plan(const HostOp &H)
     for (int f = 0; f < 4; f++) for (int s = 0; s < Nfp; s++) W.forder[(size_t)f * Nfp + s] = s;
 
     // ---- geometry records (same record as the blocked plan) --------------------------------------------------------------
-    W.geo.assign((size_t)W.NEpad * BLK_GEO, 0.0);
+    W.geo.assign((size_t)W.NEpad * WG_GEO, 0.0);
     for (int e = 0; e < W.NEpad; e++) {
-        double *g = &W.geo[(size_t)e * BLK_GEO];
+        double *g = &W.geo[(size_t)e * WG_GEO];
         if (e < NE) {
             const double *v1 = &H.geo[(size_t)e * GEO_STRIDE], *jc = &H.jac[(size_t)e * 10];
             // J / det J (covariant transform and push-forward share it), J^-1, fscale, 1/det, det/eps, det/mu, sigma/eps
