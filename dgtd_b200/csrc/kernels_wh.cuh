@@ -39,7 +39,7 @@ template <int P> struct Wh {
     static constexpr int oWarp = NFR * 32;
     static constexpr size_t bTab = (size_t)(oWarp + NW * WDBL) * 8;
     static constexpr size_t bBar = bTab + (size_t)TABROWS * 16;
-    static constexpr size_t smem_bytes = bBar + (size_t)NW * 2 * 8;
+    static constexpr size_t smem_bytes = bBar + (size_t)(NW * 2 + 1) * 8;     // per-warp barriers + one for the operator fragments
     static_assert(Np - 8 * (NT - 1) <= 4, "mixed last tile");
     static_assert((GS % 2) == 0 && (bTab % 16) == 0 && (WDBL % 2) == 0, "alignment");
 };
@@ -67,12 +67,13 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
     const int2 *wDesc = reinterpret_cast<const int2 *>(wGeo + B::WGEO);
     uint64_t *barY = reinterpret_cast<uint64_t *>(smem_wg + B::bBar) + 2 * warp, *barXZ = barY + 1;
 
-    for (int i = tid; i < B::NFR * 32; i += B::T) sm[i] = A.bfrag[i];
+    uint64_t *barF = reinterpret_cast<uint64_t *>(smem_wg + B::bBar) + 2 * B::NW;   // operator fragments: one bulk copy per CTA
     {
         uint4 *dst = reinterpret_cast<uint4 *>(smem_wg + B::bTab);
         const uint4 *src = reinterpret_cast<const uint4 *>(A.tab);
         for (int i = tid; i < min(A.ntab, B::TABROWS); i += B::T) dst[i] = src[i];
     }
+    if (tid == 0) mbar_init(barF, 1);
     if (leader) { mbar_init(barY, 1); mbar_init(barXZ, 1); }
     if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
@@ -96,7 +97,9 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
         if (LOAD_X) bulk_load(wX, (MODE == MODE_STAGE1 ? A.yin : A.x) + (size_t)gg * GS, GS * 8, barXZ);
         if (LOAD_Z) bulk_load(wZ, A.z + (size_t)gg * GS, GS * 8, barXZ);
     };
+    if (tid == 0) { mbar_expect_tx(barF, (uint32_t)(B::NFR * 32 * 8)); bulk_load(sm, A.bfrag, B::NFR * 32 * 8, barF); }
     if (leader && g < ngroups) { issue_y(g); if (LOAD_X || LOAD_Z) issue_xz(g); }
+    mbar_wait(barF, 0);
 
     for (int it = 0; g < ngroups; g += gstride, it++) {
         const uint32_t par = it & 1;
