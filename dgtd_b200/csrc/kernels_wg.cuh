@@ -165,7 +165,10 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
     using B = Wg<P>;
     constexpr int Np = B::Np, Nfp = B::Nfp, NT = B::NT, KSV = B::KSV, VT = B::VT, GS = B::GS;
     constexpr int NL = Np - 8 * (NT - 1);                                          // nodes of the mixed tile
-    constexpr int PF = P >= 4 ? 1 : 2;                                             // neighbour-record prefetch distance (face steps)
+#ifndef DGTD_WG_PF
+#define DGTD_WG_PF 3
+#endif
+    constexpr int PF = P >= 4 ? 1 : DGTD_WG_PF;                                    // neighbour-record prefetch distance (face steps)
     constexpr bool LOAD_X = MODE == MODE_STAGE1 || MODE == MODE_STAGE23;           // stage 1: x == y_in, fetched again (L2 hit)
     constexpr bool LOAD_Z = MODE == MODE_STAGE23 || MODE == MODE_STAGE4;
     constexpr bool STORE_X = MODE != MODE_STAGE4, STORE_Z = MODE != MODE_MULT;      // stage 4 forms the new x in the z buffer
