@@ -464,12 +464,13 @@ static void upload_local(dgtd_ctx *c, const double *hloc, double *dev, bool call
 {
     const long long Nl = c->Nloc;
     if (c->pushed == dev) c->pushed = nullptr;
-    if (!c->blocked) {
+    if (!c->blocked && !caller_order) {
         CU(cudaMemcpyAsync(dev, hloc, sizeof(double) * 6 * Nl, cudaMemcpyHostToDevice, c->stream));
     } else {
         if (c->stage_ref.n != (size_t)6 * Nl) c->stage_ref.alloc((size_t)6 * Nl);
         CU(cudaMemcpyAsync(c->stage_ref.p, hloc, sizeof(double) * 6 * Nl, cudaMemcpyHostToDevice, c->stream));
-        to_device_layout(c, c->stage_ref.p, dev, caller_order ? c->dgid.p : nullptr);
+        if (c->blocked) to_device_layout(c, c->stage_ref.p, dev, caller_order ? c->dgid.p : nullptr);
+        else { permute_elements_kernel<<<1184, 256, 0, c->stream>>>(c->stage_ref.p, c->dgid.p, c->H.Np, c->H.NEloc, Nl, 1, dev); c->launches++; }
     }
     CU(cudaStreamSynchronize(c->stream));
 }
@@ -477,11 +478,12 @@ static void download_local(dgtd_ctx *c, const double *dev, double *hloc, bool ca
 {
     const long long Nl = c->Nloc;
     p2p_check(c);
-    if (!c->blocked) {
+    if (!c->blocked && !caller_order) {
         CU(cudaMemcpyAsync(hloc, dev, sizeof(double) * 6 * Nl, cudaMemcpyDeviceToHost, c->stream));
     } else {
         if (c->stage_ref.n != (size_t)6 * Nl) c->stage_ref.alloc((size_t)6 * Nl);
-        from_device_layout(c, dev, c->stage_ref.p, caller_order ? c->dgid.p : nullptr);
+        if (c->blocked) from_device_layout(c, dev, c->stage_ref.p, caller_order ? c->dgid.p : nullptr);
+        else { permute_elements_kernel<<<1184, 256, 0, c->stream>>>(dev, c->dgid.p, c->H.Np, c->H.NEloc, Nl, 0, c->stage_ref.p); c->launches++; }
         CU(cudaMemcpyAsync(hloc, c->stage_ref.p, sizeof(double) * 6 * Nl, cudaMemcpyDeviceToHost, c->stream));
     }
     CU(cudaStreamSynchronize(c->stream));
@@ -491,7 +493,7 @@ static void scatter_to_device(dgtd_ctx *c, const double *host, double *dev)
 {
     const int Np = c->H.Np; const long long Ng = c->Nglob, Nl = c->Nloc;
     if (c->identity) { upload_local(c, host, dev); return; }
-    if (c->nranks == 1 && c->blocked) { upload_local(c, host, dev, true); return; }   // the permutation runs on the device
+    if (c->nranks == 1) { upload_local(c, host, dev, true); return; }   // the permutation runs on the device
     c->hostbuf.resize((size_t)6 * Nl);
     for (int comp = 0; comp < 6; comp++)
         for (int le = 0; le < c->H.NEloc; le++)
@@ -502,7 +504,7 @@ static void gather_from_device(dgtd_ctx *c, const double *dev, double *host)
 {
     const int Np = c->H.Np; const long long Ng = c->Nglob, Nl = c->Nloc;
     if (c->identity) { download_local(c, dev, host); return; }
-    if (c->nranks == 1 && c->blocked) { download_local(c, dev, host, true); return; }
+    if (c->nranks == 1) { download_local(c, dev, host, true); return; }
     c->hostbuf.resize((size_t)6 * Nl);
     download_local(c, dev, c->hostbuf.data());
     for (int comp = 0; comp < 6; comp++)

@@ -303,6 +303,20 @@ __global__ void gather_kernel(const double *x, const long long *off, long long c
         for (int c = 0; c < 6; c++) out[c * n + i] = p[c * cstride];
     }
 }
+// reference-layout vectors [6][N] in the caller's element order <-> in this rank's (Morton) element order; to_local = 1:
+// out[c][le * Np + n] = in[c][gid[le] * Np + n], 0: the inverse
+__global__ void permute_elements_kernel(const double *in, const int *gid, int Np, long long NEloc, long long stride, int to_local, double *out)
+{
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < NEloc * Np; idx += (long long)gridDim.x * blockDim.x) {
+        const long long le = idx / Np; const int n = (int)(idx - le * Np);
+        const long long other = (long long)gid[le] * Np + n;
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            if (to_local) out[c * stride + idx] = in[c * stride + other];
+            else out[c * stride + other] = in[c * stride + idx];
+        }
+    }
+}
 __global__ void pack_kernel(const double *y, long long stride, const int *send_node, int ns, double *send, long long sstride)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {
