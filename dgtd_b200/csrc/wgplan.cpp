@@ -8,7 +8,6 @@
 #include "../../include/dgtd_b200.h"
 
 #include <algorithm>
-#include <cstdlib>
 #include <map>
 
 namespace dgtd {
@@ -70,7 +69,6 @@ WgPlan build_wg_plan(const HostOp &H)
     };
 
     // ---- face descriptors ---------------------------------------------------------------------------------------------------
-    const bool dbg_nonbr = std::getenv("DGTD_B200_DBG_NONBR") != nullptr;   // timing experiment only (wrong results)
     W.desc.assign((size_t)W.NEpad * 8, 0);
     for (int e = 0; e < W.NEpad; e++)
         for (int f = 0; f < 4; f++) {
@@ -83,7 +81,6 @@ WgPlan build_wg_plan(const HostOp &H)
             if (row > FI_TAB_MASK) throw Error(DGTD_ERR_UNSUPPORTED, "too many distinct face orientations");
             code = (code & ~(FI_TAB_MASK << FI_TAB_SHIFT)) | (row << FI_TAB_SHIFT);
             fo[0] = nb; fo[1] = code;
-            if (dbg_nonbr && nb >= 0 && (nb >> 3) != (e >> 3)) { fo[0] = -1; fo[1] = 0; }   // experiment: no trace leaves the group
         }
 
     // ---- DMMA B fragments (m8n8k4: lane l holds B[k = l&3][n = l>>2]) ------------------------------------------------------
