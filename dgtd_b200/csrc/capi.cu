@@ -79,7 +79,7 @@ struct Nccl {
 };
 Nccl g_nccl;
 constexpr int NCCL_FLOAT64 = 8;   // ncclDouble
-constexpr int NCCL_UINT8 = 1, NCCL_INT32 = 2, NCCL_MIN = 3;
+constexpr int NCCL_UINT8 = 1, NCCL_INT32 = 2, NCCL_MAX = 2, NCCL_MIN = 3;
 }  // namespace
 
 template <class T> struct DevBuf {
@@ -851,7 +851,15 @@ int dgtd_run_until(dgtd_ctx *c, double *t, double dt, double t_final, int check_
             CU(cudaMemcpyAsync(&ss, c->scratch.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
             CU(cudaStreamSynchronize(c->stream));
             const double nrm = std::sqrt(ss);
-            if (!std::isfinite(nrm) || nrm > 1e20) { bad = 1; break; }   // the reference warns and goes on; here the caller decides
+            int flag = (!std::isfinite(nrm) || nrm > 1e20) ? 1 : 0;
+            if (c->nranks > 1 && c->comm) {      // all ranks must leave the loop together (Solver.cpp:503: MPI_Allreduce MAX)
+                DevBuf<int> d; d.alloc(1);
+                CU(cudaMemcpyAsync(d.p, &flag, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+                g_nccl.check(g_nccl.AllReduce(d.p, d.p, 1, NCCL_INT32, NCCL_MAX, c->comm, c->stream), "ncclAllReduce");
+                CU(cudaMemcpyAsync(&flag, d.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+            }
+            if (flag) { bad = 1; break; }        // the reference warns and goes on; here the caller decides
         }
     }
     if (nsteps) *nsteps = n;

@@ -137,7 +137,8 @@ int  dgtd_rk4_run(dgtd_ctx *, double t0, double dt, int nsteps);
 /* Solver::run (Solver.cpp:497-533) with Solver::step's final short step (Solver.cpp:535-537): advances *t from its value
  * to t_final with steps of min(dt, t_final - t).  check_every > 0 evaluates the reference's per-step stability test
  * (!isfinite(norm) || norm > 1e20, Solver.cpp:500-516) on this rank's dofs every that many steps and stops with
- * *unstable = 1 when it fires (multi-rank callers reduce the flag as the reference does with MPI_MAX).            */
+ * *unstable = 1 when it fires; on multi-rank contexts the flag is max-reduced over the ranks (the reference's
+ * MPI_Allreduce, Solver.cpp:503) so that all of them stop at the same step.                                        */
 int  dgtd_run_until(dgtd_ctx *, double *t, double dt, double t_final, int check_every, long long *nsteps, int *unstable);
 /* ||state||_2 over all ranks' owned dofs of THIS rank (caller reduces) — Fields::getNorml2        */
 int  dgtd_norm2_local(dgtd_ctx *, double *sumsq);
