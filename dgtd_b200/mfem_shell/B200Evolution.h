@@ -108,6 +108,35 @@ private:
     dgtd_ctx *ctx_ = nullptr;
 };
 
+// Probe / surface-export snapshots without stopping the time loop (replaces the six TransferMaps + host copy per export step
+// of RCSSurfaceExporter::transferFields, RCSSurfaceExporter.cpp:71-79, and the point/field probe reads of ProbesManager):
+// Launch() queues a gather kernel and an asynchronous device-to-host copy of the six fields at a fixed list of scalar dofs
+// (Fields numbering, element * Np + node), Wait() makes Data() readable: [Ex|Ey|Ez|Hx|Hy|Hz][NumLocal()].
+class B200Gather {
+public:
+    B200Gather(B200Evolution &ev, const std::vector<long long> &dofs) : ev_(ev)
+    {
+        long long n = 0;
+        B200Evolution::check(dgtd_gather_create(ev.context(), (long long)dofs.size(), dofs.data(), &g_, &n));
+        owned_.resize((size_t)n); data_.SetSize((int)(6 * n));
+        if (n) B200Evolution::check(dgtd_gather_dofs(g_, owned_.data()));
+        data_.HostWrite();
+    }
+    ~B200Gather() { dgtd_gather_destroy(g_); }
+    B200Gather(const B200Gather &) = delete;
+    B200Gather &operator=(const B200Gather &) = delete;
+    void Launch() { B200Evolution::check(dgtd_gather_launch(ev_.context(), g_, data_.HostWrite())); }
+    void Wait() { B200Evolution::check(dgtd_gather_wait(ev_.context(), g_)); }
+    long long NumLocal() const { return (long long)owned_.size(); }
+    const std::vector<long long> &OwnedDofs() const { return owned_; }      // this rank's share of the list, output order
+    const mfem::Vector &Data() const { return data_; }
+private:
+    B200Evolution &ev_;
+    dgtd_gather *g_ = nullptr;
+    std::vector<long long> owned_;
+    mfem::Vector data_;
+};
+
 class B200RK4Solver : public mfem::ODESolver {
 public:
     void Init(mfem::TimeDependentOperator &f) override
@@ -135,6 +164,16 @@ public:
         need(); if (!resident_) throw std::runtime_error("B200RK4Solver::Run: call Upload first.");
         B200Evolution::check(dgtd_rk4_run(b200_->context(), t, dt, nsteps));
         t += nsteps * dt;
+    }
+    // Solver::run (Solver.cpp:497-533) on the resident state: steps of min(dt, tFinal - t) until tFinal, the reference's
+    // stability test on the state norm every `checkEvery` steps (0: never).  Returns false when the test fired.
+    bool RunUntil(mfem::real_t &t, mfem::real_t dt, mfem::real_t tFinal, int checkEvery = 0, long long *nsteps = nullptr)
+    {
+        need(); if (!resident_) throw std::runtime_error("B200RK4Solver::RunUntil: call Upload first.");
+        double tt = t; int unstable = 0;
+        B200Evolution::check(dgtd_run_until(b200_->context(), &tt, dt, tFinal, checkEvery, nsteps, &unstable));
+        t = tt;
+        return unstable == 0;
     }
     void Download(mfem::Vector &x) { need(); if (x.Size() != b200_->Height()) x.SetSize(b200_->Height()); B200Evolution::check(dgtd_get_state(b200_->context(), x.HostWrite())); }
 

@@ -34,6 +34,8 @@ def test_mfem_shells_match_the_reference_operator(name):
     d = json.loads(r.stdout.strip().splitlines()[-1])
     tol = 1e-10   # north_star: 1e-10 relative L2 per step
     assert d["mult_rel_l2"] < tol and d["mfem_rk4_on_b200_rel_l2"] < tol and d["fused_rk4_rel_l2"] < tol and d["resident_run_rel_l2"] < tol
+    # Solver::run's final short step through B200RK4Solver::RunUntil, and a B200Gather snapshot queued before the loop
+    assert d["run_until_rel_l2"] < tol and d["gather_abs"] == 0.0
     assert d["generic_fallback_rel_l2"] == 0.0
     if name == "tfsf_planewave":
         assert d["tfsf_applied"] > 0
