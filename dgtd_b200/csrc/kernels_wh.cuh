@@ -50,7 +50,10 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
     using B = Wh<P>;
     constexpr int Np = B::Np, Nfp = B::Nfp, NT = B::NT, KSV = B::KSV, VT = B::VT, GS = B::GS;
     constexpr int NL = Np - 8 * (NT - 1);
-    constexpr int PF = 1;
+#ifndef DGTD_WH_PF
+#define DGTD_WH_PF 2
+#endif
+    constexpr int PF = DGTD_WH_PF;                      // neighbour-record prefetch distance (face steps)
     constexpr bool LOAD_X = MODE == MODE_STAGE1 || MODE == MODE_STAGE23;
     constexpr bool LOAD_Z = MODE == MODE_STAGE23 || MODE == MODE_STAGE4;
     constexpr bool STORE_X = MODE != MODE_STAGE4, STORE_Z = MODE != MODE_MULT;
