@@ -83,7 +83,10 @@ typedef struct dgtd_options {
 int  dgtd_mesh_from_arrays(int dim, int nv, const double *verts, int ne, const int *elems,
                            const int *elem_attr, int nbe, const int *bdr, const int *bdr_attr,
                            dgtd_mesh **out);
-/* Gmsh 2.2 ASCII (.msh, attribute = physical tag as MFEM reads it) or "MFEM mesh v1.0" (.mesh).   */
+/* Gmsh 2.2 ASCII (.msh, attribute = physical tag as MFEM reads it) or "MFEM mesh v1.0" (.mesh).  Elements keep the file's
+ * order; for "MFEM mesh v1.0" the arrays equal what mfem::Mesh holds after loading, for Gmsh files MFEM renumbers the
+ * vertices, so state vectors are interchangeable with the reference's only when the mesh comes from the reference's
+ * mfem::Mesh through dgtd_mesh_from_arrays (what B200Evolution does).                                               */
 int  dgtd_mesh_load(const char *path, dgtd_mesh **out);
 /* nx*ny*nz cubes of 6 tetrahedra on [0,sx]x[0,sy]x[0,sz]; boundary attributes 1..6 =
  * bottom(z=0), front(y=0), right(x=sx), back(y=sy), left(x=0), top(z=sz) (MFEM's MakeCartesian3D). */

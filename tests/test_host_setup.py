@@ -251,3 +251,74 @@ def test_boundary_element_listing_for_surface_exports():
     ext = [a for a in set(np.asarray(pb.bdr_attr).tolist()) if a not in tags]
     p2 = mesh.boundary_elements(ext)
     assert len(p2) == int(np.isin(pb.bdr_attr, ext).sum())
+
+
+def test_mfem_mesh_reader_reproduces_what_mfem_loads():
+    """dgtd_mesh_load on an `MFEM mesh v1.0` file against the arrays MFEM itself produced for the same file (stored in the
+    TF/SF fixtures by the reference-based oracle, after Mesh::LoadFromFile(..., fix_orientation = true))."""
+    pb, _ = load_golden("tfsf3d_p2_on")
+    m = dg.Mesh.load(os.path.join(ROOT, "tests", "golden", "tfsf_box.mesh"))
+    v, e, ea, b, ba = m.arrays()
+    assert (m.dim, m.ne, m.nbe) == (3, len(pb.elems), len(pb.bdr))
+    assert np.array_equal(v, pb.verts) and np.array_equal(ea, pb.elem_attr)
+    assert np.array_equal(e, pb.elems)                      # same vertex order as MFEM after its orientation fix
+    assert np.array_equal(np.sort(b, axis=1), np.sort(np.asarray(pb.bdr), axis=1)) and np.array_equal(ba, pb.bdr_attr)
+
+
+def test_gmsh_reader_on_a_hand_written_file(tmp_path):
+    """Gmsh 2.2 ASCII: nodes, tetrahedra (type 4) with physical tag -> element attribute, triangles (type 2) -> boundary
+    elements; an inverted tetrahedron is re-oriented like MFEM does (mesh.cpp:6437-6493)."""
+    p = tmp_path / "two_tets.msh"
+    p.write_text("""$MeshFormat
+2.2 0 8
+$EndMeshFormat
+$Nodes
+5
+1 0 0 0
+2 1 0 0
+3 0 1 0
+4 0 0 1
+5 1 1 1
+$EndNodes
+$Elements
+5
+1 2 2 7 1 1 2 3
+2 2 2 7 1 1 2 4
+3 2 2 9 2 2 3 5
+4 4 2 1 1 1 2 3 4
+5 4 2 2 2 2 4 3 5
+$EndElements
+""")
+    m = dg.Mesh.load(str(p))
+    v, e, ea, b, ba = m.arrays()
+    assert (m.dim, m.nv, m.ne, m.nbe) == (3, 5, 2, 3)
+    assert ea.tolist() == [1, 2] and sorted(ba.tolist()) == [7, 7, 9]
+    for t in e:                                             # positive orientation after loading
+        J = (v[t[1:]] - v[t[0]]).T
+        assert np.linalg.det(J) > 0
+    assert sorted(map(sorted, e.tolist())) == [[0, 1, 2, 3], [1, 2, 3, 4]]
+    # the operator setup accepts it (shared face found, boundary tags resolved)
+    d = dg.setup_query(m, "dims", np.int32, order=2, bdr={7: dg.BC_PEC, 9: dg.BC_SMA})
+    assert d[5] == 2
+    with pytest.raises(dg.DgtdError):
+        dg.Mesh.load(str(tmp_path / "missing.msh"))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/testData/maxwellInputs/2D_PEC/2D_PEC.msh"), reason="needs /root/reference (build container)")
+def test_gmsh_reader_on_the_reference_config2_mesh():
+    """The reference's own 2D_PEC.msh through dgtd_mesh_load against MFEM's view of it (config-2 fixture)."""
+    pb, _ = load_golden("config2_2d_pec_p3")
+    m = dg.Mesh.load("/root/reference/testData/maxwellInputs/2D_PEC/2D_PEC.msh")
+    v, e, ea, b, ba = m.arrays()
+    assert (m.dim, m.ne, m.nbe) == (2, len(pb.elems), len(pb.bdr))
+    # MFEM renumbers the Gmsh nodes, so compare geometry: element k covers the same three points, in the same element order
+    canon = lambda pts: np.array(sorted(map(tuple, np.round(pts, 12))))
+    mine, theirs = v[e], pb.verts[np.asarray(pb.elems)]
+    assert all(np.array_equal(canon(a), canon(c)) for a, c in zip(mine, theirs))
+    assert np.array_equal(ea, pb.elem_attr)
+    key = lambda V, B, A: sorted((tuple(map(tuple, canon(V[f]))), int(t)) for f, t in zip(B, A))
+    assert key(v, b, ba) == key(pb.verts, np.asarray(pb.bdr), pb.bdr_attr)
+    # and the operator setup sees the same problem: every element's geometry factors agree with the oracle's on MFEM's arrays
+    O = HesthavenOracle(pb)
+    d = dg.setup_query(m, "dims", np.int32, order=3, bdr={1: dg.BC_PMC, 2: dg.BC_PEC, 3: dg.BC_PMC, 4: dg.BC_PEC})
+    assert d[5] == O.NE
