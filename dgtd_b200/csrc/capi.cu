@@ -1054,6 +1054,10 @@ int dgtd_setup_query(const dgtd_mesh *mesh, const dgtd_options *o, const char *n
         WP = build_wg_plan(H);
         if (n == "wg_hpush") { src = WP.hpush.data(); bytes = WP.hpush.size() * 4; }
         else if (n == "wg_tab") { src = WP.tab.data(); bytes = WP.tab.size(); }
+        else if (n == "wg_dims") { dims = {WP.ngroups, WP.NEpad, WP.NT, WP.KSV, WP.nfrag_vol, WP.nfrag_lift, WP.ntab, WG_GEO}; src = dims.data(); bytes = dims.size() * 4; }
+        else if (n == "wg_bfrag") { src = WP.bfrag.data(); bytes = WP.bfrag.size() * 8; }
+        else if (n == "wg_geo") { src = WP.geo.data(); bytes = WP.geo.size() * 8; }
+        else if (n == "wg_forder") { src = WP.forder.data(); bytes = WP.forder.size() * 4; }
         else if (n == "wg_desc") { src = WP.desc.data(); bytes = WP.desc.size() * 4; }
         else if (n == "wg_send_off") { src = WP.send_off.data(); bytes = WP.send_off.size() * 8; }
         else if (n == "wg_dev2ref") { src = WP.dev2ref.data(); bytes = WP.dev2ref.size() * 4; }

@@ -8,6 +8,9 @@
 #include "../../include/dgtd_b200.h"
 
 #include <algorithm>
+#include <cstdlib>
+#include <functional>
+#include <string>
 #include <map>
 
 namespace dgtd {
@@ -23,11 +26,70 @@ WgPlan build_wg_plan(const HostOp &H)
     const int NT = W.NT = (Np + 7) / 8, KSV = W.KSV = (Np + 3) / 4;
     if (Np - 8 * (NT - 1) > 4) throw Error(DGTD_ERR_UNSUPPORTED, "the mixed last tile holds at most 4 output nodes");
 
-    // ---- device node numbering and per-face step order (identity; hooks for bank-conflict-free orders) ----------------
+    // ---- device node numbering and per-face step order ------------------------------------------------------------------
+    // default ("file"): the reference element's numbering, face nodes in ascending order.
+    // DGTD_B200_FACE_ORDER=bank: at face step s the four lanes (e, j = 0..3) of an element gather the node records
+    // tab[j][s]; with 48-byte records an LDS.128 of a quarter warp (two elements x four faces) is conflict-free exactly when
+    // the four node ids are distinct mod 4.  So the nodes are renumbered into four residue classes whose face incidences sum
+    // to Nfp each, and every step takes one node of each class (a perfect matching of faces and classes; it exists at every
+    // step because the face x class incidence counts form a regular bipartite multigraph).
     W.dev2ref.resize(Np); W.ref2dev.resize(Np);
     for (int n = 0; n < Np; n++) W.dev2ref[n] = W.ref2dev[n] = n;
     W.forder.resize((size_t)4 * Nfp);
     for (int f = 0; f < 4; f++) for (int s = 0; s < Nfp; s++) W.forder[(size_t)f * Nfp + s] = s;
+    const char *fo_env = std::getenv("DGTD_B200_FACE_ORDER");
+    if (fo_env && std::string(fo_env) == "bank") {
+        std::vector<int> mult(Np, 0);
+        for (int f = 0; f < 4; f++) for (int s = 0; s < Nfp; s++) mult[H.ref.fnodes[(size_t)f * Nfp + s]]++;
+        // how many nodes of each face multiplicity (3: vertices, 2: edge nodes, 1: face nodes, 0: interior) go into each
+        // residue class: class r holds cap[r] nodes whose multiplicities sum to Nfp (a search over counts, not over nodes)
+        int cap[4], have[4] = {0, 0, 0, 0}, x[4][4];
+        for (int r = 0; r < 4; r++) cap[r] = (Np - r + 3) / 4;
+        for (int n = 0; n < Np; n++) have[mult[n]]++;
+        std::function<bool(int)> fill = [&](int r) {
+            if (r == 4) return have[0] == 0 && have[1] == 0 && have[2] == 0 && have[3] == 0;
+            for (int a = 0; a <= have[3]; a++)
+                for (int b = 0; b <= have[2]; b++) {
+                    const int c = Nfp - 3 * a - 2 * b, d = cap[r] - a - b - c;
+                    if (c < 0 || c > have[1] || d < 0 || d > have[0]) continue;
+                    x[r][3] = a; x[r][2] = b; x[r][1] = c; x[r][0] = d;
+                    have[3] -= a; have[2] -= b; have[1] -= c; have[0] -= d;
+                    if (fill(r + 1)) return true;
+                    have[3] += a; have[2] += b; have[1] += c; have[0] += d;
+                }
+            return false;
+        };
+        std::vector<int> cls(Np, -1);
+        auto place = [&](int) {
+            if (!fill(0)) return false;
+            for (int r = 0; r < 4; r++)
+                for (int m = 0; m < 4; m++)
+                    for (int n = 0; n < Np && x[r][m] > 0; n++)
+                        if (cls[n] < 0 && mult[n] == m) { cls[n] = r; x[r][m]--; }
+            return true;
+        };
+        if (place(0)) {
+            int next[4] = {0, 1, 2, 3};
+            for (int n = 0; n < Np; n++) { W.ref2dev[n] = next[cls[n]]; W.dev2ref[next[cls[n]]] = n; next[cls[n]] += 4; }
+            std::vector<char> used((size_t)4 * Nfp, 0);
+            int cnt[4][4] = {};
+            for (int f = 0; f < 4; f++) for (int s = 0; s < Nfp; s++) cnt[f][cls[H.ref.fnodes[(size_t)f * Nfp + s]]]++;
+            for (int s = 0; s < Nfp; s++) {
+                int perm[4] = {0, 1, 2, 3}, pick[4] = {-1, -1, -1, -1};
+                do {
+                    bool ok = true;
+                    for (int f = 0; f < 4; f++) ok &= cnt[f][perm[f]] > 0;
+                    if (ok) { for (int f = 0; f < 4; f++) pick[f] = perm[f]; break; }
+                } while (std::next_permutation(perm, perm + 4));
+                if (pick[0] < 0) throw Error(DGTD_ERR_UNSUPPORTED, "face-step matching failed");
+                for (int f = 0; f < 4; f++) {
+                    cnt[f][pick[f]]--;
+                    for (int m = 0; m < Nfp; m++)
+                        if (!used[(size_t)f * Nfp + m] && cls[H.ref.fnodes[(size_t)f * Nfp + m]] == pick[f]) { used[(size_t)f * Nfp + m] = 1; W.forder[(size_t)f * Nfp + s] = m; break; }
+                }
+            }
+        }
+    }
 
     // ---- geometry records (same record as the blocked plan) --------------------------------------------------------------
     W.geo.assign((size_t)W.NEpad * WG_GEO, 0.0);

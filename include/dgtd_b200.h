@@ -193,7 +193,7 @@ int  dgtd_halo_bytes(const dgtd_ctx *, long long *bytes);
 
 /* Host-only diagnostic (no CUDA, no compute): copies one of the flat tables a rank would upload — "dims", "D", "lift",
  * "nodes", "fnodes", "geo", "finfo", "ftab", "elem_gid", "tfsf_xyz", "gate_xyz", "tfsf_side", "send_node", "peers", "peers5",
- * "node_coords", the plan of the warp-per-group kernel "wg_hpush", "wg_tab", "wg_desc", "wg_send_off", "wg_dev2ref", and for tetrahedra the plan of the tensor-core kernel "blk_dims", "blk_geo", "blk_desc", "blk_afrag",
+ * "node_coords", the plan of the warp-per-group kernel "wg_dims", "wg_bfrag", "wg_geo", "wg_forder", "wg_hpush", "wg_tab", "wg_desc", "wg_send_off", "wg_dev2ref", and for tetrahedra the plan of the tensor-core kernel "blk_dims", "blk_geo", "blk_desc", "blk_afrag",
  * "blk_send_off" — so that tests can check the setup against the oracle without a GPU.                            */
 int  dgtd_setup_query(const dgtd_mesh *, const dgtd_options *, const char *name, void *buf, long long cap_bytes, long long *size_bytes);
 
