@@ -11,13 +11,14 @@ from conftest import load_golden, product_mesh_and_kwargs, rel_l2
 from oracle.dgtd_oracle import HesthavenOracle
 
 
-def _plan(mesh, kw):
-    q = lambda name, dt: dg.setup_query(mesh, name, dt, **kw)
+def _plan(mesh, kw, **extra):
+    q = lambda name, dt: dg.setup_query(mesh, name, dt, **kw, **extra)
     ngroups, NEpad, NT, KSV, nfv, nfl, ntab, GEO = q("wg_dims", np.int32)
     return dict(NT=NT, KSV=KSV, nfv=nfv, nfl=nfl, NEpad=NEpad,
                 bfrag=q("wg_bfrag", np.float64).reshape(-1, 32), geo=q("wg_geo", np.float64).reshape(NEpad, GEO),
                 desc=q("wg_desc", np.int32).reshape(NEpad, 4, 2), tab=q("wg_tab", np.uint8).reshape(-1, 16),
-                d2r=q("wg_dev2ref", np.int32), gid=q("elem_gid", np.int32), dims=q("dims", np.int32))
+                d2r=q("wg_dev2ref", np.int32), gid=q("elem_gid", np.int32), dims=q("dims", np.int32),
+                hpush=q("wg_hpush", np.int32).reshape(-1, 2), peers=q("peers5", np.int32).reshape(-1, 5))
 
 
 def _frag_matrix(f):
@@ -28,8 +29,30 @@ def _frag_matrix(f):
     return B
 
 
-def replay_mult(P, x_ref, alpha):
-    """Mult(x) (no TF/SF source, single rank) from the plan tables."""
+def device_state(P, x_ref):
+    """u[e][device node][c] of this rank's elements from a global reference-layout vector."""
+    Np, NE = P["dims"][2], P["dims"][5]
+    xr = x_ref.reshape(6, -1)
+    U = np.zeros((NE, Np, 6))
+    for le in range(NE):
+        U[le] = xr[:, P["gid"][le] * Np + P["d2r"]].T
+    return U
+
+
+def pushed_traces(P, U):
+    """What the stage kernel stores into its neighbours' halo buffers: {peer rank: {slot on the peer: [Nfp][6]}} —
+    face behind my halo slot s, my nodes in the RECEIVER's face-node order (row hpush[s] >> 8 of the tables)."""
+    Nfp = P["dims"][3]
+    slot_face = {-2 - P["desc"][e, f, 0]: (e, f) for e in range(P["dims"][5]) for f in range(4) if P["desc"][e, f, 0] < -1}
+    out = {}
+    for s, (e, f) in slot_face.items():
+        pi, row = P["hpush"][s, 0] & 0xff, P["hpush"][s, 0] >> 8
+        out.setdefault(int(P["peers"][pi, 0]), {})[int(P["hpush"][s, 1])] = U[e, P["tab"][row, :Nfp]]
+    return out
+
+
+def replay_mult(P, x_ref, alpha, halo=None):
+    """Mult(x) (no TF/SF source) from the plan tables; halo = {my halo slot: [Nfp][6]} on a multi-rank plan."""
     dim, p, Np, Nfp, nf, NE = P["dims"][:6]
     NT, KSV, VT = P["NT"], P["KSV"], (P["NT"] - 1) * 3 + 3
     NL = Np - 8 * (NT - 1)
@@ -37,11 +60,7 @@ def replay_mult(P, x_ref, alpha):
     fragL = [_frag_matrix(f) for f in P["bfrag"][P["nfv"]:P["nfv"] + P["nfl"]]]
     d2r, gid, tab = P["d2r"], P["gid"], P["tab"]
     N = x_ref.size // 6
-    xr = x_ref.reshape(6, N)
-    # device state u[e][n_dev][c]
-    U = np.zeros((NE, Np, 6))
-    for le in range(NE):
-        U[le] = xr[:, gid[le] * Np + d2r].T
+    U = device_state(P, x_ref)
     K = np.zeros_like(U)
     for e in range(NE):
         g = P["geo"][e]
@@ -75,10 +94,12 @@ def replay_mult(P, x_ref, alpha):
             nb, code = P["desc"][e, j]
             ce = ch = 0.0
             al = alpha
+            trace = None
             if nb >= 0:
                 nrow, ne_ = tab[(code >> 4) & 0xff], nb
+            elif nb < -1:                                # partition face: the neighbour rank's trace, canonical node order
+                trace, nrow = halo[-2 - nb], tab[4 + j]
             else:
-                assert nb == -1, "single-rank replay"
                 bc = code & 3
                 ce = -2.0 if bc == 1 else -1.0 if bc == 3 else 0.0
                 ch = -2.0 if bc == 2 else -1.0 if bc == 3 else 0.0
@@ -92,7 +113,8 @@ def replay_mult(P, x_ref, alpha):
             Ah = Jim @ cross
             Ae = af * (Jim - np.outer(Jim @ gn, gn) / fs[j] ** 2)
             for s in range(Nfp):
-                uM, uP = U[e, tab[j][s]], U[ne_, nrow[s]]
+                uM = U[e, tab[j][s]]
+                uP = trace[nrow[s]] if trace is not None else U[ne_, nrow[s]]
                 dE = uP[:3] - (1.0 - ce) * uM[:3]
                 dH = uP[3:] - (1.0 - ch) * uM[3:]
                 ft[s, j, :3] = Ah @ dH + Ae @ dE
@@ -146,3 +168,33 @@ def test_plan_replay_matches_the_oracle(name, face_order, monkeypatch):
         own = P["tab"][:4, :Nfp].astype(int)
         assert sorted(P["d2r"].tolist()) == list(range(P["dims"][2]))
         assert all(len(set(own[:, s] % 4)) == 4 for s in range(Nfp)), "a face step with a bank conflict"
+
+
+@pytest.mark.parametrize("name,world,method", [("box3d_p3_pec_upwind", 2, "rcb"), ("box3d_p3_pec_upwind", 4, "metis"), ("box3d_p2_mixed_centered", 3, "rcb")])
+def test_partitioned_plan_replay_with_pushed_traces(name, world, method):
+    """The peer-memory halo path on the CPU: every rank 'stores' the traces of its partition faces into the slots of its
+    neighbours' halo buffers as the stage kernel would (hpush tables), then evaluates its share from its own plan; the
+    assembled result must be the oracle's Mult on the undivided mesh."""
+    pb, _ = load_golden(name)
+    mesh, kw = product_mesh_and_kwargs(pb)
+    kw = {k: v for k, v in kw.items() if k in ("order", "alpha", "bdr", "materials")}
+    O = HesthavenOracle(pb)
+    x = np.random.default_rng(21).standard_normal(6 * O.N)
+    part = mesh.partition(world, method)
+    plans = [_plan(mesh, kw, rank=r, nranks=world, partitioning=part) for r in range(world)]
+    halos = [dict() for _ in range(world)]
+    for r, P in enumerate(plans):
+        for peer, slots in pushed_traces(P, device_state(P, x)).items():
+            halos[peer].update(slots)
+    out = np.zeros(6 * O.N)
+    owned = np.zeros(O.N, int)
+    for r, P in enumerate(plans):
+        n_halo = sum(1 for e in range(P["dims"][5]) for f in range(4) if P["desc"][e, f, 0] < -1)
+        assert sorted(halos[r]) == list(range(n_halo)), "every halo slot of a rank is written exactly by its neighbours"
+        k = replay_mult(P, x, pb.alpha, halos[r]).reshape(6, -1)
+        Np = P["dims"][2]
+        idx = (P["gid"][:, None] * Np + np.arange(Np)[None, :]).ravel()
+        out.reshape(6, -1)[:, idx] = k[:, idx]
+        owned[idx] += 1
+    assert owned.min() == 1 and owned.max() == 1
+    assert rel_l2(out, O.mult(0.0, x)) < 1e-12
