@@ -7,8 +7,6 @@
 #include "../../include/dgtd_b200.h"
 #include "host.hpp"
 #include "kernels.cuh"
-#include "kernels_mma.cuh"
-#include "kernels_ws.cuh"
 #include "kernels_wg.cuh"
 #include "kernels_wh.cuh"
 
@@ -116,40 +114,6 @@ static KernelSet select_kernels(int dim, int p)
     throw Error(DGTD_ERR_UNSUPPORTED, "no kernel for this dimension/order");
 }
 
-typedef void (*MmaFn)(const MmaArgs);
-struct MmaSet { MmaFn fn[4]; int threads; size_t smem; };
-template <int P, int G> static MmaSet mset()
-{
-    using B = Blk<P, G>;
-    return {{stage_mma_kernel<P, G, 0>, stage_mma_kernel<P, G, 1>, stage_mma_kernel<P, G, 2>, stage_mma_kernel<P, G, 3>}, B::T, B::smem_bytes};
-}
-// the DMMA kernel covers tetrahedra of order 1..4 (order 5 does not fit the shared-memory tiling: generic kernel);
-// G = element groups (of 8) per CTA batch
-static bool select_mma(int dim, int p, int G, MmaSet &ms)
-{
-    if (dim != 3) return false;
-    switch (p * 10 + G) {
-        case 11: ms = mset<1, 1>(); return true; case 21: ms = mset<2, 1>(); return true;
-        case 31: ms = mset<3, 1>(); return true; case 41: ms = mset<4, 1>(); return true;
-        case 32: ms = mset<3, 2>(); return true; case 22: ms = mset<2, 2>(); return true;
-    }
-    return false;
-}
-
-// the warp-specialised kernel: tetrahedra of order 2..3 without conductivity, 16-element batches, one CTA per SM
-template <int P> static MmaSet wsset()
-{
-    using B = Ws<P>;
-    return {{stage_ws_kernel<P, 0>, stage_ws_kernel<P, 1>, stage_ws_kernel<P, 2>, stage_ws_kernel<P, 3>}, B::T, B::smem_bytes};
-}
-static bool select_ws(int dim, int p, MmaSet &ms)
-{
-    if (dim != 3) return false;
-    if (p == 3) { ms = wsset<3>(); return true; }
-    if (p == 2) { ms = wsset<2>(); return true; }
-    return false;
-}
-
 // the warp-per-group kernel: tetrahedra of order 1..4, element-major "aos" layout, one warp per group of 8 elements
 typedef void (*WgFn)(const WgArgs);
 struct WgSet { WgFn fn[4]; int threads; size_t smem; };
@@ -189,20 +153,16 @@ static bool select_wh(int dim, int p, bool tf, WgSet &ws, int &groups_per_cta)
 
 struct dgtd_ctx {
     HostOp H;
-    BlockedPlan BP;
     WgPlan WP;
     bool has_sigma = false;
     bool wh = false;                 // ... or its half-row form (kernels_wh.cuh, groups of 4 elements); wg stays set: same plan and layout
     int wg_groups_per_cta = 0;
-    bool wg = false;                 // aos layout + warp-per-group kernel (blocked is set too: state needs layout conversion)
+    bool wg = false;                 // aos layout + warp-per-group kernel (the state needs a layout conversion at the ABI)
     WgSet wgs{};
     DevBuf<uint8_t> wtab;
     DevBuf<int> dev2ref;
-    bool blocked = false;            // state lives in the blocked layout and the DMMA stage kernel runs
-    bool ws = false;                 // ... its warp-specialised variant
     bool identity = true;            // local element order == global order (single rank, no reordering)
-    long long Nalloc = 0;            // scalar dofs allocated per component (padded to whole batches when blocked)
-    MmaSet ms{};
+    long long Nalloc = 0;            // scalar dofs allocated per component (padded to whole groups of 8 elements in the aos layout)
     DevBuf<double> bgeo, bafrag, stage_ref;
     DevBuf<int> bdesc;
     DevBuf<long long> bsend_off;
@@ -227,17 +187,17 @@ struct dgtd_ctx {
     size_t p2p_peer_hb[P2P_MAXPEERS] = {};
     unsigned long long epoch = 0;                    // exchanges produced so far (all ranks run the same sequence)
     const double *pushed = nullptr;                  // vector whose traces exchange `epoch` carries (nullptr: none valid)
-    DevBuf<unsigned int> p2p_done;
+    DevBuf<unsigned int> p2p_done, p2p_cnt;         // last-CTA election of the stand-alone push kernel; per-peer arrival counters of the fused push
+    DevBuf<int> worder;                              // WgPlan::order (multi-rank contexts: partition-face groups first)
     DevBuf<int> p2p_err;
     DevBuf<int> hpush, dgid;                         // dgid: local element -> caller's element index (H.elem_gid)
     long long launches = 0;
-    std::vector<double> hostbuf;     // pinned staging would go here; plain vector for gather/scatter by element
-    ~dgtd_ctx()
-    {
-        for (void *b : p2p_peer_base) if (b) cudaIpcCloseMemHandle(b);
-        if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
-        if (own_stream) cudaStreamDestroy(own_stream);
-    }
+    std::vector<double> hostbuf;     // staging of the by-element gather/scatter of multi-rank contexts
+    DevBuf<int> flagbuf;             // one int: collective verdicts (run_until's stability flag, teardown barriers)
+    DevBuf<int> smp_elem;            // dgtd_sample staging, grown on demand (point probes are called every step)
+    DevBuf<double> smp_shape, smp_out;
+    std::vector<struct dgtd_gather *> gathers;       // live gathers: their device resources go with the context
+    ~dgtd_ctx();
 };
 
 static void fill_args(dgtd_ctx *c, StageArgs &A)
@@ -256,8 +216,8 @@ static void exchange(dgtd_ctx *c, const double *y)
     if (!c->comm) throw Error(DGTD_ERR_COMM, "multi-rank context used before dgtd_comm_init");
     const int Nfp = c->H.Nfp;
     const int ns = c->H.n_halo_faces * Nfp;
-    if (c->blocked) {   // node records [face][node][6], one contiguous message per peer
-        pack_blocked_kernel<<<std::min(1024, (3 * ns + 255) / 256), 256, 0, c->stream>>>(y, c->bsend_off.p, ns, c->sendbuf.p);
+    if (c->wg) {   // node records [face][node][6], one contiguous message per peer
+        pack_records_kernel<<<std::min(1024, (3 * ns + 255) / 256), 256, 0, c->stream>>>(y, c->bsend_off.p, ns, c->sendbuf.p);
         c->launches++;
         g_nccl.check(g_nccl.GroupStart(), "ncclGroupStart");
         for (auto &pp : c->H.peers) {
@@ -294,8 +254,9 @@ static void p2p_setup(dgtd_ctx *c)
         c->p2p_hb = (((size_t)c->H.n_halo_faces * c->H.Nfp * 6 * sizeof(double)) + 127) / 128 * 128;
         c->p2p_mem.alloc(4096 + 2 * c->p2p_hb + 128);
         CU(cudaMemset(c->p2p_mem.p, 0, c->p2p_mem.n));
-        c->p2p_done.alloc(1); c->p2p_err.alloc(1);
+        c->p2p_done.alloc(1); c->p2p_err.alloc(1); c->p2p_cnt.alloc(P2P_MAXPEERS);
         CU(cudaMemset(c->p2p_done.p, 0, sizeof(unsigned int))); CU(cudaMemset(c->p2p_err.p, 0, sizeof(int)));
+        CU(cudaMemset(c->p2p_cnt.p, 0, P2P_MAXPEERS * sizeof(unsigned int)));
         if (cudaIpcGetMemHandle(&mine.h, c->p2p_mem.p) != cudaSuccess) { cudaGetLastError(); want = 0; }
         mine.hb = c->p2p_hb;
     }
@@ -328,14 +289,14 @@ static void p2p_setup(dgtd_ctx *c)
     }
     c->p2p = true; c->epoch = 0; c->pushed = nullptr;
 }
-// all ranks' kernels must have drained before any rank unmaps or frees a halo buffer its neighbours store into
-static void p2p_quiesce(dgtd_ctx *c)
+// collective barrier on the context's stream (teardown: all ranks' kernels must have drained before any rank unmaps or
+// frees a halo buffer its neighbours store into).  No allocation, no exception: it runs inside dgtd_destroy.
+static void comm_barrier(dgtd_ctx *c)
 {
-    if (!c->p2p || !c->comm) return;
+    if (!c->comm || !c->flagbuf.p) return;
     cudaStreamSynchronize(c->stream);
-    DevBuf<int> d; d.alloc(1);
-    cudaMemsetAsync(d.p, 0, sizeof(int), c->stream);
-    g_nccl.AllReduce(d.p, d.p, 1, NCCL_INT32, NCCL_MIN, c->comm, c->stream);
+    cudaMemsetAsync(c->flagbuf.p, 0, sizeof(int), c->stream);
+    g_nccl.AllReduce(c->flagbuf.p, c->flagbuf.p, 1, NCCL_INT32, NCCL_MIN, c->comm, c->stream);
     cudaStreamSynchronize(c->stream);
 }
 static void p2p_check(dgtd_ctx *c)
@@ -368,7 +329,8 @@ static WgP2P p2p_args(dgtd_ctx *c, unsigned long long wait, unsigned long long s
         q.peer_flag[p] = reinterpret_cast<unsigned long long *>(base) + c->H.peers[p].remote_idx;
     }
     q.wait_epoch = wait; q.signal_epoch = signal;
-    q.done = c->p2p_done.p; q.err = c->p2p_err.p;
+    q.done = c->p2p_done.p; q.cnt = c->p2p_cnt.p; q.err = c->p2p_err.p;
+    for (int p = 0; p < q.npeers; p++) q.need[p] = c->wh ? c->WP.need4[(size_t)p] : c->WP.need8[(size_t)p];
     return q;
 }
 static const double *p2p_halo_in(dgtd_ctx *c, unsigned long long k)
@@ -383,7 +345,7 @@ static void launch_stage(dgtd_ctx *c, int mode, StageArgs &A)
         if (c->pushed != A.yin) {   // the traces of y_in are not at the peers yet: stand-alone producer of the next exchange
             const int nrec = c->H.n_halo_faces * c->H.Nfp;
             c->epoch++;
-            halo_push_kernel<<<std::min(296, (nrec + 127) / 128), 128, 0, c->stream>>>(A.yin, c->bsend_off.p, nrec, c->H.Nfp, p2p_args(c, 0, c->epoch));
+            halo_push_kernel<<<std::min(296, (nrec + 127) / 128), 128, 0, c->stream>>>(A.yin, c->bsend_off.p, nrec, c->H.Nfp, p2p_args(c, c->epoch - 1, c->epoch));
             c->launches++;
             c->pushed = A.yin;
         }
@@ -398,15 +360,10 @@ static void launch_stage(dgtd_ctx *c, int mode, StageArgs &A)
         }
         W.bfrag = c->bafrag.p; W.geo = c->bgeo.p; W.desc = c->bdesc.p; W.tab = c->wtab.p; W.ntab = c->WP.ntab;
         W.tfsf_xyz = A.tfsf_xyz; W.gate = A.gate; W.halo = A.halo; W.ngroups = c->WP.ngroups; W.has_sigma = c->has_sigma ? 1 : 0;
+        W.order = c->nranks > 1 ? c->worder.p : nullptr;
         W.alpha = A.alpha; W.pw = A.pw; W.pw_on = A.pw_on;
         W.yin = A.yin; W.x = A.x; W.z = A.z; W.yout = A.yout; W.a = A.a; W.b = A.b; W.t = A.t;
         c->wgs.fn[mode]<<<c->grid, c->wgs.threads, c->wgs.smem, c->stream>>>(W);
-    } else if (c->blocked) {
-        MmaArgs M;
-        M.afrag = c->bafrag.p; M.geo = c->bgeo.p; M.desc = c->bdesc.p; M.ftab = c->ftab.p; M.ntab = c->H.ntab;
-        M.tfsf_xyz = A.tfsf_xyz; M.gate = A.gate; M.halo = A.halo; M.nbatch = c->BP.nbatch; M.alpha = A.alpha; M.pw = A.pw; M.pw_on = A.pw_on;
-        M.yin = A.yin; M.x = A.x; M.z = A.z; M.yout = A.yout; M.a = A.a; M.b = A.b; M.t = A.t;
-        c->ms.fn[mode]<<<c->grid, c->ms.threads, c->ms.smem, c->stream>>>(M);
     } else {
         c->ks.fn[mode]<<<c->grid, c->ks.threads, c->ks.smem, c->stream>>>(A);
     }
@@ -443,33 +400,31 @@ static void mult_device(dgtd_ctx *c, double t, const double *in, double *out)
     launch_stage(c, MODE_MULT, A);
 }
 
-// reference-layout device vector [6][Nloc] <-> the kernel's state layout (blocked, or aos for the warp-per-group kernel);
+// reference-layout device vector [6][Nloc] <-> the aos state layout of the warp-per-group kernels;
 // gid: the vector is in the caller's element order (single rank) and the Morton permutation is applied on the fly
 static void to_device_layout(dgtd_ctx *c, const double *ref, double *dev, const int *gid = nullptr)
 {
-    if (c->wg) to_aos_kernel<<<1184, 256, 0, c->stream>>>(ref, c->Nloc, c->H.Np, c->H.NEloc, c->WP.NEpad, c->dev2ref.p, gid, dev);
-    else to_blocked_kernel<<<1184, 256, 0, c->stream>>>(ref, c->Nloc, c->H.Np, c->H.NEloc, c->BP.NEpad, gid, dev);
+    to_aos_kernel<<<1184, 256, 0, c->stream>>>(ref, c->Nloc, c->H.Np, c->H.NEloc, c->WP.NEpad, c->dev2ref.p, gid, dev);
     c->launches++;
 }
 static void from_device_layout(dgtd_ctx *c, const double *dev, double *ref, const int *gid = nullptr)
 {
-    if (c->wg) from_aos_kernel<<<1184, 256, 0, c->stream>>>(dev, c->Nloc, c->H.Np, c->H.NEloc, c->dev2ref.p, gid, ref);
-    else from_blocked_kernel<<<1184, 256, 0, c->stream>>>(dev, c->Nloc, c->H.Np, c->H.NEloc, gid, ref);
+    from_aos_kernel<<<1184, 256, 0, c->stream>>>(dev, c->Nloc, c->H.Np, c->H.NEloc, c->dev2ref.p, gid, ref);
     c->launches++;
 }
 
-// host vector [6][Nloc] <-> device state (reference layout, or blocked/aos through a staging buffer).  caller_order: the
+// host vector [6][Nloc] <-> device state (reference layout, or aos through a staging buffer).  caller_order: the
 // host vector is in the caller's (global) element order of a single-rank context
 static void upload_local(dgtd_ctx *c, const double *hloc, double *dev, bool caller_order = false)
 {
     const long long Nl = c->Nloc;
     if (c->pushed == dev) c->pushed = nullptr;
-    if (!c->blocked && !caller_order) {
+    if (!c->wg && !caller_order) {
         CU(cudaMemcpyAsync(dev, hloc, sizeof(double) * 6 * Nl, cudaMemcpyHostToDevice, c->stream));
     } else {
         if (c->stage_ref.n != (size_t)6 * Nl) c->stage_ref.alloc((size_t)6 * Nl);
         CU(cudaMemcpyAsync(c->stage_ref.p, hloc, sizeof(double) * 6 * Nl, cudaMemcpyHostToDevice, c->stream));
-        if (c->blocked) to_device_layout(c, c->stage_ref.p, dev, caller_order ? c->dgid.p : nullptr);
+        if (c->wg) to_device_layout(c, c->stage_ref.p, dev, caller_order ? c->dgid.p : nullptr);
         else { permute_elements_kernel<<<1184, 256, 0, c->stream>>>(c->stage_ref.p, c->dgid.p, c->H.Np, c->H.NEloc, Nl, 1, dev); c->launches++; }
     }
     CU(cudaStreamSynchronize(c->stream));
@@ -478,11 +433,11 @@ static void download_local(dgtd_ctx *c, const double *dev, double *hloc, bool ca
 {
     const long long Nl = c->Nloc;
     p2p_check(c);
-    if (!c->blocked && !caller_order) {
+    if (!c->wg && !caller_order) {
         CU(cudaMemcpyAsync(hloc, dev, sizeof(double) * 6 * Nl, cudaMemcpyDeviceToHost, c->stream));
     } else {
         if (c->stage_ref.n != (size_t)6 * Nl) c->stage_ref.alloc((size_t)6 * Nl);
-        if (c->blocked) from_device_layout(c, dev, c->stage_ref.p, caller_order ? c->dgid.p : nullptr);
+        if (c->wg) from_device_layout(c, dev, c->stage_ref.p, caller_order ? c->dgid.p : nullptr);
         else { permute_elements_kernel<<<1184, 256, 0, c->stream>>>(dev, c->dgid.p, c->H.Np, c->H.NEloc, Nl, 0, c->stage_ref.p); c->launches++; }
         CU(cudaMemcpyAsync(hloc, c->stage_ref.p, sizeof(double) * 6 * Nl, cudaMemcpyDeviceToHost, c->stream));
     }
@@ -559,7 +514,7 @@ int dgtd_mesh_from_arrays(int dim, int nv, const double *verts, int ne, const in
     m->m.elems.assign(elems, elems + (size_t)ne * (dim + 1));
     if (elem_attr) m->m.elem_attr.assign(elem_attr, elem_attr + ne); else m->m.elem_attr.assign(ne, 1);
     if (nbe) { m->m.bdr.assign(bdr, bdr + (size_t)nbe * dim); m->m.bdr_attr.assign(bdr_attr, bdr_attr + nbe); }
-    m->m.validate_and_orient();
+    m->m.validate_and_orient(false);     // the caller's element-local order is a contract: inverted elements are rejected, not swapped
     *out = m.release();
     GUARD_END
 }
@@ -632,28 +587,23 @@ int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
     c->Nloc = (long long)H.NEloc * H.Np; c->Nglob = H.NEglob * H.Np;
     c->identity = c->nranks == 1;
     for (int le = 0; le < H.NEloc && c->identity; le++) c->identity = H.elem_gid[le] == le;
-    // kernel choice: DGTD_B200_KERNEL = wg | ws | mma | generic overrides the default (wg, the fastest eligible one)
+    // kernel choice: DGTD_B200_KERNEL = wg | wh | generic overrides the default
     const char *kenv = std::getenv("DGTD_B200_KERNEL");
     const std::string ksel = kenv ? kenv : "";
-    const char *groups = std::getenv("DGTD_B200_GROUPS");               // tuning of the mma kernel: element groups per CTA batch
-    int G = groups ? std::atoi(groups) : 1;
     bool has_sigma = false;
     for (int le = 0; le < H.NEloc; le++) has_sigma |= H.geo[(size_t)le * GEO_STRIDE + 15] != 0.0;
     c->has_sigma = has_sigma;
-    const bool tabs_ok = H.ntab <= 128;
     const bool has_tf = H.pw.enabled && H.n_tfsf_faces > 0;
-    // default: the warp-pair kernel at order 4 (8 instead of 4 warps per SM: 69 vs 60 G DOF-updates/s), the one-warp kernel
-    // below it (at order 3 the pair's doubled fragment / trace loads make it shared-memory bound: 82 vs 110 G)
-    // default: the half-row kernel at order 4 (8 instead of 4 warps per SM: 77 vs 60 G DOF-updates/s), the one-warp-per-8
-    // kernel below it (order 3: 109 vs 107 G, order 2: 102 vs 91 G)
+    // default for tetrahedra: the half-row kernel at order 4 (8 instead of 4 warps per SM), the one-warp-per-8-elements
+    // kernel below it; everything else (segments, triangles, order-5 tetrahedra): the generic kernel
     if ((ksel == "wh" || (ksel.empty() && H.p == 4)) && select_wh(H.dim, H.p, has_tf, c->wgs, c->wg_groups_per_cta) && c->wgs.smem <= (size_t)prop.sharedMemPerBlockOptin) {
         c->WP = build_wg_plan(H);
-        if (c->WP.ntab <= Wg<3>::TABROWS) c->blocked = c->wg = c->wh = true;
+        if (c->WP.ntab <= Wg<3>::TABROWS) c->wg = c->wh = true;
     }
     if (!c->wg && (ksel == "wg" || ksel == "wh" || ksel.empty()) && select_wg(H.dim, H.p, has_tf, c->wgs) && c->wgs.smem <= (size_t)prop.sharedMemPerBlockOptin) {
         c->WP = build_wg_plan(H);
         c->wg_groups_per_cta = c->wgs.threads / 32;
-        if (c->WP.ntab <= Wg<3>::TABROWS) c->blocked = c->wg = true;
+        if (c->WP.ntab <= Wg<3>::TABROWS) c->wg = true;
     }
     if (c->wg) {
         c->Nalloc = (long long)c->WP.NEpad * H.Np;
@@ -663,20 +613,9 @@ int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
         c->grid = (int)std::min<long long>((units + nw - 1) / nw, (long long)prop.multiProcessorCount);
         c->bgeo.upload(c->WP.geo); c->bafrag.upload(c->WP.bfrag); c->bdesc.upload(c->WP.desc); c->bsend_off.upload(c->WP.send_off, 1);
         c->wtab.upload(c->WP.tab, 16); c->dev2ref.upload(c->WP.dev2ref); c->hpush.upload(c->WP.hpush, 2);
-    } else if (ksel != "generic" && tabs_ok) {
-        if (ksel != "mma" && !has_sigma && select_ws(H.dim, H.p, c->ms) && c->ms.smem <= (size_t)prop.sharedMemPerBlockOptin) { c->blocked = c->ws = true; G = 2; }
-        else if (select_mma(H.dim, H.p, G, c->ms) || select_mma(H.dim, H.p, G = 1, c->ms)) c->blocked = c->ms.smem <= (size_t)prop.sharedMemPerBlockOptin;
-    }
-    if (c->wg) {
-    } else if (c->blocked) {
-        c->BP = build_blocked_plan(H, G);
-        c->Nalloc = (long long)c->BP.NEpad * H.Np;
-        for (int m = 0; m < 4; m++) CU(cudaFuncSetAttribute((const void *)c->ms.fn[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ms.smem));
-        int occ = 0; CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)c->ms.fn[2], c->ms.threads, c->ms.smem));
-        if (occ < 1) throw Error(DGTD_ERR_UNSUPPORTED, "DMMA stage kernel does not fit on an SM");
-        c->grid = (int)std::min<long long>(c->BP.nbatch, (long long)prop.multiProcessorCount * (c->ws ? 1 : occ));
-        c->bgeo.upload(c->BP.geo); c->bafrag.upload(c->BP.afrag); c->bdesc.upload(c->BP.desc); c->bsend_off.upload(c->BP.send_off, 1);
+        if (c->nranks > 1) c->worder.upload(c->WP.order, 1);
     } else {
+        if (H.ntab > 256) throw Error(DGTD_ERR_UNSUPPORTED, "too many distinct face orientations for the generic kernel");
         c->Nalloc = c->Nloc;
         c->ks = select_kernels(H.dim, H.p);
         if (c->ks.smem > (size_t)prop.sharedMemPerBlockOptin) throw Error(DGTD_ERR_UNSUPPORTED, "order too high for the shared-memory tiling");
@@ -703,7 +642,7 @@ int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
     c->send_node.upload(H.send_node, 1);
     c->dgid.upload(H.elem_gid, 1);
     const size_t hn = std::max<size_t>(1, (size_t)6 * H.n_halo_faces * H.Nfp);
-    c->halo.alloc(hn); c->sendbuf.alloc(hn); c->scratch.alloc(4);
+    c->halo.alloc(hn); c->sendbuf.alloc(hn); c->scratch.alloc(4); c->flagbuf.alloc(1);
     CU(cudaMemset(c->halo.p, 0, hn * sizeof(double)));
     const size_t n6 = (size_t)6 * c->Nalloc;
     c->x.alloc(n6); c->ya.alloc(n6); c->yb.alloc(n6); c->z.alloc(n6);
@@ -722,9 +661,11 @@ int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
 void dgtd_destroy(dgtd_ctx *c)
 {
     if (!c) return;
-    cudaSetDevice(c->device);
-    p2p_quiesce(c);
-    delete c;
+    try {
+        cudaSetDevice(c->device);
+        delete c;               // ~dgtd_ctx: collective teardown of the halo mappings (two barriers), then the device memory
+    } catch (...) {             // nothing may cross the C ABI
+    }
 }
 int dgtd_sizes(const dgtd_ctx *c, long long *n_global, int *np, long long *ne_local, long long *n_local)
 {
@@ -798,7 +739,7 @@ int dgtd_mult(dgtd_ctx *c, double t, const double *in, double *out, int on_devic
     CU(cudaSetDevice(c->device));
     const size_t n6 = (size_t)6 * c->Nalloc;
     c->pushed = nullptr;   // tmp_in / a caller-owned vector is about to change under the same address
-    if (on_device && !c->blocked) { mult_device(c, t, in, out); }
+    if (on_device && !c->wg) { mult_device(c, t, in, out); }
     else {
         if (c->tmp_in.n != n6) { c->tmp_in.alloc(n6); c->tmp_out.alloc(n6); }
         if (on_device) {   // reference-layout device vectors [6][n_local] <-> blocked
@@ -853,10 +794,10 @@ int dgtd_run_until(dgtd_ctx *c, double *t, double dt, double t_final, int check_
             const double nrm = std::sqrt(ss);
             int flag = (!std::isfinite(nrm) || nrm > 1e20) ? 1 : 0;
             if (c->nranks > 1 && c->comm) {      // all ranks must leave the loop together (Solver.cpp:503: MPI_Allreduce MAX)
-                DevBuf<int> d; d.alloc(1);
-                CU(cudaMemcpyAsync(d.p, &flag, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-                g_nccl.check(g_nccl.AllReduce(d.p, d.p, 1, NCCL_INT32, NCCL_MAX, c->comm, c->stream), "ncclAllReduce");
-                CU(cudaMemcpyAsync(&flag, d.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+                int *d = c->flagbuf.p;
+                CU(cudaMemcpyAsync(d, &flag, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+                g_nccl.check(g_nccl.AllReduce(d, d, 1, NCCL_INT32, NCCL_MAX, c->comm, c->stream), "ncclAllReduce");
+                CU(cudaMemcpyAsync(&flag, d, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
                 CU(cudaStreamSynchronize(c->stream));
             }
             if (flag) { bad = 1; break; }        // the reference warns and goes on; here the caller decides
@@ -885,12 +826,11 @@ int dgtd_sample(dgtd_ctx *c, int npts, const int *elem, const double *shape, dou
     if (npts == 0) return DGTD_OK;
     for (int p = 0; p < npts; p++) if (elem[p] < 0 || elem[p] >= c->H.NEloc) throw Error(DGTD_ERR_ARG, "probe element out of range");
     CU(cudaSetDevice(c->device));
-    DevBuf<int> de; DevBuf<double> ds, dout;
-    de.alloc(npts); ds.alloc((size_t)npts * c->H.Np); dout.alloc((size_t)npts * 6);
+    DevBuf<int> &de = c->smp_elem; DevBuf<double> &ds = c->smp_shape, &dout = c->smp_out;
+    if (de.n < (size_t)npts) { de.alloc(npts); ds.alloc((size_t)npts * c->H.Np); dout.alloc((size_t)npts * 6); }
     CU(cudaMemcpyAsync(de.p, elem, sizeof(int) * npts, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(ds.p, shape, sizeof(double) * npts * c->H.Np, cudaMemcpyHostToDevice, c->stream));
     if (c->wg) sample_aos_kernel<<<(npts + 127) / 128, 128, 0, c->stream>>>(c->x.p, c->H.Np, npts, de.p, ds.p, c->dev2ref.p, dout.p);
-    else if (c->blocked) sample_blocked_kernel<<<(npts + 127) / 128, 128, 0, c->stream>>>(c->x.p, c->H.Np, npts, de.p, ds.p, dout.p);
     else sample_kernel<<<(npts + 127) / 128, 128, 0, c->stream>>>(c->x.p, c->Nloc, c->H.Np, npts, de.p, ds.p, dout.p);
     c->launches++;
     CU(cudaMemcpyAsync(out6, dout.p, sizeof(double) * npts * 6, cudaMemcpyDeviceToHost, c->stream));
@@ -898,7 +838,8 @@ int dgtd_sample(dgtd_ctx *c, int npts, const int *elem, const double *shape, dou
     GUARD_END
 }
 struct dgtd_gather {
-    dgtd_ctx *c = nullptr;
+    dgtd_ctx *c = nullptr;                // nullptr once the context is gone (dgtd_destroy before dgtd_gather_destroy)
+    int device = 0;
     std::vector<long long> dofs;          // owned dofs, global numbering, output order
     DevBuf<long long> off;                // offset of component 0 in the device state
     long long cstride = 1;
@@ -906,13 +847,31 @@ struct dgtd_gather {
     cudaStream_t side = nullptr;
     cudaEvent_t ready = nullptr, done = nullptr;
     bool pending = false;
-    ~dgtd_gather()
+    void release_device()                 // streams, events and buffers live on the context's device
     {
-        if (done) { if (pending) cudaEventSynchronize(done); cudaEventDestroy(done); }
-        if (ready) cudaEventDestroy(ready);
-        if (side) cudaStreamDestroy(side);
+        if (done) { if (pending) cudaEventSynchronize(done); cudaEventDestroy(done); done = nullptr; }
+        if (ready) { cudaEventDestroy(ready); ready = nullptr; }
+        if (side) { cudaStreamDestroy(side); side = nullptr; }
+        off.release(); stage.release(); pending = false;
     }
+    ~dgtd_gather() { release_device(); }
 };
+dgtd_ctx::~dgtd_ctx()
+{
+    for (dgtd_gather *g : gathers) { g->release_device(); g->c = nullptr; }     // a later dgtd_gather_destroy only frees the shell
+    if (p2p && comm) {
+        // neighbours store into my halo buffer and I into theirs: (1) everybody's kernels have drained, (2) everybody has
+        // closed its mappings of the others' buffers, only then is an exported buffer freed (cudaFree of memory a peer
+        // still maps is undefined)
+        comm_barrier(this);
+        for (void *&b : p2p_peer_base) if (b) { cudaIpcCloseMemHandle(b); b = nullptr; }
+        comm_barrier(this);
+        p2p_mem.release();
+    }
+    for (void *b : p2p_peer_base) if (b) cudaIpcCloseMemHandle(b);
+    if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+    if (own_stream) cudaStreamDestroy(own_stream);
+}
 
 int dgtd_gather_create(dgtd_ctx *c, long long n, const long long *dofs, dgtd_gather **out, long long *n_local)
 {
@@ -923,7 +882,7 @@ int dgtd_gather_create(dgtd_ctx *c, long long n, const long long *dofs, dgtd_gat
     std::vector<int> g2l((size_t)c->H.NEglob, -1);
     for (int le = 0; le < c->H.NEloc; le++) g2l[(size_t)c->H.elem_gid[le]] = le;
     auto g = std::make_unique<dgtd_gather>();
-    g->c = c;
+    g->c = c; g->device = c->device;
     std::vector<long long> off;
     for (long long i = 0; i < n; i++) {
         const long long d = dofs[i];
@@ -932,16 +891,16 @@ int dgtd_gather_create(dgtd_ctx *c, long long n, const long long *dofs, dgtd_gat
         if (le < 0) continue;   // another rank's
         g->dofs.push_back(d);
         if (c->wg) off.push_back(((long long)le * Np + c->WP.ref2dev[node]) * 6);
-        else if (c->blocked) off.push_back(blocked_offset(Np, le, node));
         else off.push_back((long long)le * Np + node);
     }
-    g->cstride = c->blocked ? 1 : c->Nloc;
+    g->cstride = c->wg ? 1 : c->Nloc;
     g->off.upload(off, 1);
     g->stage.alloc(std::max<size_t>(1, 6 * off.size()));
     CU(cudaStreamCreateWithFlags(&g->side, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&g->ready, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&g->done, cudaEventDisableTiming));
     if (n_local) *n_local = (long long)g->dofs.size();
+    c->gathers.push_back(g.get());
     *out = g.release();
     GUARD_END
 }
@@ -979,7 +938,11 @@ int dgtd_gather_wait(dgtd_ctx *c, dgtd_gather *g)
 void dgtd_gather_destroy(dgtd_gather *g)
 {
     if (!g) return;
-    if (g->c) cudaSetDevice(g->c->device);
+    if (g->c) {                            // context still alive: free the device side now and leave its list
+        cudaSetDevice(g->device);
+        auto &v = g->c->gathers;
+        for (size_t i = 0; i < v.size(); i++) if (v[i] == g) { v.erase(v.begin() + (long)i); break; }
+    }
     delete g;
 }
 int dgtd_mesh_boundary_elements(const dgtd_mesh *m, int n_attr, const int *bdr_attr, long long cap_pairs, int *pairs, long long *n_pairs)
@@ -1015,9 +978,6 @@ int dgtd_kernel_info(const dgtd_ctx *c, char *buf, int cap)
     else if (c->wg)
         std::snprintf(tmp, sizeof tmp, "stage_wg_kernel<P=%d,MODE> DMMA m8n8k4 transposed, warp per group of 8 elements, aos layout, %d threads, %zu B smem, grid %d%s",
                       c->H.p, c->wgs.threads, c->wgs.smem, c->grid, c->nranks == 1 ? "" : c->p2p ? ", halo: fused peer-memory stores" : ", halo: NCCL send/recv");
-    else if (c->blocked)
-        std::snprintf(tmp, sizeof tmp, "%s<P=%d,G=%d,MODE> DMMA m8n8k4, blocked layout, %d threads, %zu B smem, grid %d",
-                      c->ws ? "stage_ws_kernel" : "stage_mma_kernel", c->H.p, c->BP.G, c->ms.threads, c->ms.smem, c->grid);
     else
         std::snprintf(tmp, sizeof tmp, "stage_kernel<DIM=%d,P=%d,MODE> generic, %d threads, %zu B smem, grid %d", c->H.dim, c->H.p, c->ks.threads, c->ks.smem, c->grid);
     std::snprintf(buf, (size_t)cap, "%s", tmp);
@@ -1061,20 +1021,12 @@ int dgtd_setup_query(const dgtd_mesh *mesh, const dgtd_options *o, const char *n
         else if (n == "wg_desc") { src = WP.desc.data(); bytes = WP.desc.size() * 4; }
         else if (n == "wg_send_off") { src = WP.send_off.data(); bytes = WP.send_off.size() * 8; }
         else if (n == "wg_dev2ref") { src = WP.dev2ref.data(); bytes = WP.dev2ref.size() * 4; }
+        else if (n == "wg_order") { src = WP.order.data(); bytes = WP.order.size() * 4; }
+        else if (n == "wg_need") { dims = WP.need8; dims.insert(dims.end(), WP.need4.begin(), WP.need4.end()); dims.push_back(WP.nfront); src = dims.data(); bytes = dims.size() * 4; }
         else throw Error(DGTD_ERR_ARG, "unknown setup table " + n);
     }
     else if (n == "dims") { dims = {H.dim, H.p, H.Np, H.Nfp, H.nf, H.NEloc, H.ntab, H.n_tfsf_faces, H.n_halo_faces}; src = dims.data(); bytes = dims.size() * 4; }
     else if (n == "node_coords") { node_coords(mesh->m, H.ref, xyz); src = xyz.data(); bytes = xyz.size() * 8; }
-    else if (n.rfind("blk_", 0) == 0) {   // tables of the DMMA kernel's plan (tetrahedra), one group per batch
-        static thread_local BlockedPlan BP;
-        BP = build_blocked_plan(H, 1);
-        if (n == "blk_dims") { dims = {BP.G, BP.ngroups, BP.nbatch, BP.NEpad, BP.slots, BP.MT, BP.KSV, BP.KSL, BP.desc_stride}; src = dims.data(); bytes = dims.size() * 4; }
-        else if (n == "blk_geo") { src = BP.geo.data(); bytes = BP.geo.size() * 8; }
-        else if (n == "blk_desc") { src = BP.desc.data(); bytes = BP.desc.size() * 4; }
-        else if (n == "blk_afrag") { src = BP.afrag.data(); bytes = BP.afrag.size() * 8; }
-        else if (n == "blk_send_off") { src = BP.send_off.data(); bytes = BP.send_off.size() * 8; }
-        else throw Error(DGTD_ERR_ARG, "unknown setup table " + n);
-    }
     else throw Error(DGTD_ERR_ARG, "unknown setup table " + n);
     *size_bytes = (long long)bytes;
     if (buf) { if ((long long)bytes > cap_bytes) throw Error(DGTD_ERR_ARG, "buffer too small"); if (bytes) std::memcpy(buf, src, bytes); }

@@ -25,7 +25,7 @@ struct Mesh {
     int nv() const { return (int)(verts.size() / 3); }
     int ne() const { return (int)elem_attr.size(); }
     int nbe() const { return (int)bdr_attr.size(); }
-    void validate_and_orient();                // simplex check, swap v0/v1 of inverted elements (mfem/mesh/mesh.cpp:6437-6493)
+    void validate_and_orient(bool reorient = true);   // simplex check; swap v0/v1 of inverted elements (mfem/mesh/mesh.cpp:6437-6493) or reject them
 };
 Mesh load_mesh(const std::string &path);
 Mesh cartesian3d(int nx, int ny, int nz, double sx, double sy, double sz);
@@ -109,33 +109,16 @@ struct HostOp {
 HostOp build_host_op(const Mesh &m, const Options &o);
 std::vector<int> boundary_element_faces(const Mesh &m, const std::vector<int> &attrs);
 
-// ---- "blocked" plan of the DMMA stage kernel (3-D only) ----------------------------------------------------------------
-// Device state layout: groups of 8 consecutive local elements; group g holds Np*8*6 doubles indexed [node j][e8][comp c]
-// (a node's six field components are contiguous: one 48-byte record).  A batch = G groups is what one CTA pass handles.
-constexpr int BLK_E = 8;               // elements per group (= DMMA n dimension)
-constexpr int BLK_GEO = 32;            // doubles per element: J[9] (dx_d/dxi_a at 3d+a), Jinv[9] (dxi_a/dx_d at 9+3a+d),
-                                       //   fscale[4] at 18, 1/detJ at 22, 1/eps 23, 1/mu 24, sigma/eps 25
-struct BlockedPlan {
-    int G = 1;                         // groups per batch
-    int ngroups = 0, nbatch = 0, NEpad = 0;
-    int slots = 0;                     // trace slots per batch (= 4 * 8 * G, the worst case)
-    int MT = 0, KSV = 0, KSL = 0;      // m-tiles, k-steps of one volume half (D_x), k-steps of LIFT
-    std::vector<double> geo;           // NEpad * BLK_GEO
-    int desc_stride = 0;               // ints per batch descriptor block
-    std::vector<int> desc;             // nbatch*desc_stride : finfo int2[8G*4], tdesc int2[slots], tcount, 3 pad (see blocked.cpp)
-    std::vector<double> afrag;         // DMMA A fragments: D_x [3][MT][KSV][32] then 0.5*LIFT [MT][KSL][32]
-    std::vector<long long> send_off;   // nSendFaces*Nfp : offset (doubles) of the node record in the blocked state
-};
-BlockedPlan build_blocked_plan(const HostOp &H, int G);
-inline long long blocked_offset(int Np, long long le, int node) { return (((le >> 3) * Np + node) * BLK_E + (le & 7)) * 6; }
+constexpr int BLK_E = 8;               // elements per group (= DMMA m dimension of the transposed contraction)
 // ---- "wg" plan of the warp-per-group DMMA stage kernel (3-D only) --------------------------------------------------------
 // Device state layout "aos": element-major node records, offset(e, n, c) = ((e * Np) + n) * 6 + c with n the DEVICE node
 // id (dev2ref maps it to the reference node); 8 consecutive local elements form a group = one warp's unit of work, one
 // contiguous chunk of Np*8*6 doubles.  The contraction runs "transposed" (DMMA A = data [8 elements x 4 nodes],
 // B = operator [4 nodes x 8 output nodes]) so that a lane owns one element through all phases.
-// geometry record stride of the wg / wh kernels: the 26 doubles of BLK_GEO's record padded to 34, so that the records of the
-// 8 elements of a group start 4 banks apart in shared memory (a stride of 32 doubles puts them all on the same banks: every
-// geometry LDS.128 cost 8 wavefronts instead of 1)
+// geometry record of the wg / wh kernels, 26 doubles: J / det J (dx_d/dxi_a at 3d+a), Jinv[9] (dxi_a/dx_d at 9+3a+d),
+// fscale[4] at 18, 1/det J at 22, det/eps 23, det/mu 24, sigma/eps 25, 1/fscale[4] at 26 — padded to a stride of 34 so that the records of
+// the 8 elements of a group start 4 banks apart in shared memory (a stride of 32 doubles puts them all on the same banks:
+// every geometry LDS.128 cost 8 wavefronts instead of 1)
 constexpr int WG_GEO = 34;
 struct WgPlan {
     int ngroups = 0, NEpad = 0;
@@ -144,12 +127,15 @@ struct WgPlan {
     std::vector<int> dev2ref, ref2dev; // Np
     std::vector<int> forder;           // 4*Nfp : step s of face f handles canonical face node forder[f*Nfp+s]
     std::vector<double> geo;           // NEpad * WG_GEO
-    std::vector<int> desc;             // NEpad*4*2 : {nbr local element | -1 boundary | -2-haloFace, code (FI_TAB = row of tab)}
+    std::vector<int> desc;             // NEpad*4*2 : {nbr local element | -1 boundary | -2-haloFace, code (FI_TAB = row of tab; partition faces: peer index)}
     std::vector<uint8_t> tab;          // ntab*16 : rows 0..3 own device node per step, 4..7 canonical index per step, 8.. neighbour device node per step
     int ntab = 0;
     std::vector<double> bfrag;         // (nfrag_vol + nfrag_lift) * 32
     std::vector<long long> send_off;   // nSendFaces*Nfp : offset (doubles) of the node record in the aos state
     std::vector<int> hpush;            // nHaloFaces*2 : {peer index | tab row << 8 (own device node per RECEIVER face node), slot on the peer}
+    std::vector<int> order;            // ngroups : processing order of the groups, the nfront groups owning a partition face first
+    int nfront = 0;
+    std::vector<int> need8, need4;     // per peer: groups of 8 / of 4 elements that push traces to it (flag raised by the last one)
 };
 WgPlan build_wg_plan(const HostOp &H);
 void node_coords(const Mesh &m, const RefElem &ref, std::vector<double> &xyz);   // [NE*Np][3], global numbering

@@ -1,9 +1,9 @@
 // sm_100a warp-per-group DMMA stage kernel (tetrahedra): one warp carries a group of 8 elements through the whole fused
 // stage — covariant transform, volume contraction, face flux, LIFT, push-forward, Runge-Kutta update — in registers.
 //
-// Why (profiles/r1_ws_stage_ncu_summary.txt): the role-specialised kernel moves every intermediate (covariant field,
-// flux, partial results) through shared memory between warps, which puts the LSU pipe at 54 % next to an FP64 pipe at
-// 61 % and leaves both waiting on hand-over barriers.  Here the contraction is TRANSPOSED: the DMMA A operand is the data
+// Why: kernels that hand intermediates (covariant field, flux, partial results) from warp to warp through
+// shared memory put the LSU pipe at 54 % next to an FP64 pipe at 61 % and left both waiting on hand-over barriers
+// (round-1 measurements, 70-81 G DOF-updates/s).  Here the contraction is TRANSPOSED: the DMMA A operand is the data
 // [8 elements x 4 nodes] and the B operand the operator [4 nodes x 8 output nodes], so lane (e = l>>2, j = l&3) owns
 // element e as A-row, as accumulator row and in the element-wise phases:
 //   volume   lane reads the node record (e, 4ks + j) of y_in, forms u~ = J^T u / det J in registers, feeds it as A;
@@ -19,15 +19,19 @@
 // Reference semantics: src/evolution/HesthavenEvolution.cpp:450-542 with the `global` operator's coefficients
 // (src/components/DGOperatorFactory.h:469-573, 1268-1361), external/mfem-geg/linalg/ode.cpp:109-136.
 #pragma once
-#include "kernels_mma.cuh"
+#include "kernels.cuh"
+#include "host.hpp"
+#include "ptx.cuh"
 
 namespace dgtd {
 
 // Direct halo exchange over NVLink peer memory (one process per GPU, buffers mapped with CUDA IPC): the stage kernel that
 // PRODUCES y_out stores the traces of its partition faces straight into the neighbour rank's halo buffer, and the kernel
-// that CONSUMES them waits, only in the warps that own a partition face, for the neighbour's epoch flag.  Exchange number k
-// uses halo buffer k & 1 on every rank; a rank signals k after ALL its stores of exchange k (last-CTA election), which is
-// also after its reads of exchange k-1, so two buffers are enough (see capi.cu: p2p_* for the host side).
+// that CONSUMES them waits, only in the lanes that own a partition face, for that neighbour's epoch flag.  Exchange number k
+// uses halo buffer k & 1 on every rank.  A rank raises peer p's flag to k after all its stores of exchange k TO p; the
+// groups that store to p are exactly the groups that read p's traces of exchange k-1 (same faces, flux before epilogue), so
+// the flag also says "my reads of your block of exchange k-1 are over" and two buffers are enough.  The groups owning
+// partition faces are processed first in a launch (WgPlan::order), so the flags are up long before the consumer asks.
 // Replaces GlobalEvolution.cpp:763-774 (six blocking MPI exchanges of whole neighbour elements per Mult).
 constexpr int P2P_MAXPEERS = 8;
 struct WgP2P {
@@ -37,7 +41,9 @@ struct WgP2P {
     const unsigned long long *flags;                     // my flag slots, one per peer
     int npeers;
     unsigned long long wait_epoch, signal_epoch;         // 0: nothing to wait for / nothing to produce
-    unsigned int *done;                                  // CTA counter of the last-CTA election
+    unsigned int *cnt;                                   // per-peer arrival counters of the fused push (stage kernels)
+    int need[P2P_MAXPEERS];                              // units (groups) of this launch that push traces to each peer
+    unsigned int *done;                                  // CTA counter of the last-CTA election (stand-alone push kernel)
     int *err;                                            // set when a wait timed out
 };
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
@@ -56,18 +62,51 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-// lanes 0..npeers-1 of the calling warp wait for their peer's flag; 20 s without progress sets *err and gives up
+__device__ __forceinline__ void p2p_spin(const WgP2P &pp, int peer)
+{
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys(pp.flags + peer) < pp.wait_epoch) {
+        if (globaltimer_ns() - t0 > 20000000000ull) { atomicExch(pp.err, 1); break; }     // 20 s without progress: give up
+    }
+}
+// lanes 0..npeers-1 of the calling warp wait for their peer's flag (stand-alone push kernel: all peers)
 __device__ __forceinline__ void p2p_wait(const WgP2P &pp, int lane)
 {
-    if (lane < pp.npeers) {
-        const unsigned long long t0 = globaltimer_ns();
-        while (ld_acquire_sys(pp.flags + lane) < pp.wait_epoch) {
-            if (globaltimer_ns() - t0 > 20000000000ull) { atomicExch(pp.err, 1); break; }
-        }
-    }
+    if (lane < pp.npeers) p2p_spin(pp, lane);
     __syncwarp();
 }
-// after the last store of the CTA: make them visible system-wide, elect the last CTA of the grid, signal every peer
+// Consumer side of a stage kernel: a lane that owns a partition face waits for THAT peer's flag (mypeer = -1: no such
+// face); `ready` is the warp-uniform set of peers already seen at wait_epoch, so every peer is polled once per warp.
+__device__ __forceinline__ unsigned p2p_wait_peers(const WgP2P &pp, int mypeer, unsigned ready)
+{
+    const bool must = mypeer >= 0 && !((ready >> mypeer) & 1u);
+    if (__any_sync(0xffffffffu, must)) {
+        if (must) p2p_spin(pp, mypeer);
+        ready |= __reduce_or_sync(0xffffffffu, must ? 1u << mypeer : 0u);
+    }
+    return ready;
+}
+// Producer side of a stage kernel, called by a whole warp after its lanes stored the traces of their partition faces
+// (mypeer = -1: this lane stored nothing): one arrival per distinct peer of the group; the warp that brings a peer's
+// counter to need[peer] raises that peer's flag, i.e. a neighbour is signalled as soon as the LAST unit touching it is done,
+// not at the end of the launch.  The elected lane's system-scope fence is cumulative over the other lanes' stores
+// (ordered before it by the warp barrier), as in a grid barrier (bar; fence; atomic).
+__device__ __forceinline__ void p2p_arrive(const WgP2P &pp, int mypeer, int lane)
+{
+    __syncwarp();
+    const unsigned same = __match_any_sync(0xffffffffu, mypeer);
+    if (mypeer >= 0 && lane == __ffs(same) - 1) {
+        __threadfence_system();
+        const unsigned prev = atomicAdd(pp.cnt + mypeer, 1u);
+        if (prev + 1u == (unsigned)pp.need[mypeer]) {
+            pp.cnt[mypeer] = 0;                          // nobody else arrives for this peer before the next launch
+            __threadfence_system();
+            st_release_sys(pp.peer_flag[mypeer], pp.signal_epoch);
+        }
+    }
+}
+// stand-alone push kernel: after the last store of the CTA make them visible system-wide, elect the last CTA of the grid,
+// signal every peer
 __device__ __forceinline__ void p2p_signal(const WgP2P &pp)
 {
     __threadfence_system();
@@ -91,6 +130,7 @@ struct WgArgs {
     const double *tfsf_xyz;
     const double *gate;
     const double *halo;       // [haloFace][Nfp][6]
+    const int *order;         // WgPlan::order (nullptr: groups in memory order)
     int ngroups;
     int has_sigma;
     double alpha;
@@ -155,7 +195,7 @@ __device__ __forceinline__ void store_rec(double *p, const double *u)
 
 // The first PF neighbour records of a face are requested BEFORE the volume contraction (their L2 latency hides behind it)
 // and the prefetch then runs PF face steps ahead; the flux is one 6x6 map per (element, face):
-//   F~_E = Ah dH + Ae dE,  F~_H = -Ah dE + Ae dH,  Ah = J^-1 [n x],  Ae = alpha fs J^-1 (I - n n^T / fs^2).
+//   F~_E = Ah (dH - na x dE),  F~_H = -Ah (dE + na x dH),  Ah = J^-1 [fs n x],  na = alpha n.
 // Measured alternatives (profiles/): one-step prefetch issued inside the face loop with the flux in physical
 // components, 97.9 G vs 110 G; asm-volatile (pinned) prefetch loads, +-0; prefetch.global.L1 of the records, -9 %.
 // TF: the context has a TF/SF plane-wave source (the injection code sits in the face loop only then).
@@ -195,29 +235,44 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
     __syncthreads();
 
     const int gstride = gridDim.x * B::NW;
-    int g = blockIdx.x * B::NW + warp;
-    const bool has_work = g < A.ngroups;
-    bool halo_ready = A.pp.wait_epoch == 0;
+    int idx = blockIdx.x * B::NW + warp;                 // position in the processing order
+    const bool has_work = idx < A.ngroups;
+    int g = has_work && A.order ? A.order[idx] : idx;
+    unsigned peers_ready = A.pp.wait_epoch == 0 ? 0xffffffffu : 0u;
     const uint4 ownrow = sTab[j];
     const bool inject = A.pw_on && (A.gate == nullptr || *A.gate >= 1e-16);
 
+#ifdef DGTD_L2_HINTS
+    const uint64_t polKeep = l2_policy_evict_last(), polOnce = l2_policy_evict_first();
+#endif
     auto issue_y = [&](int gg) {
         mbar_expect_tx(barY, (uint32_t)(GS * 8 + B::WGEO * 8 + B::WDESC * 4));
         bulk_load(wY, A.yin + (size_t)gg * GS, GS * 8, barY);
+#ifdef DGTD_L2_HINTS
+        bulk_load_hint(wGeo, A.geo + (size_t)gg * B::WGEO, B::WGEO * 8, barY, polKeep);
+        bulk_load_hint(wGeo + B::WGEO, A.desc + (size_t)gg * B::WDESC, B::WDESC * 4, barY, polKeep);
+#else
         bulk_load(wGeo, A.geo + (size_t)gg * B::WGEO, B::WGEO * 8, barY);
         bulk_load(wGeo + B::WGEO, A.desc + (size_t)gg * B::WDESC, B::WDESC * 4, barY);
+#endif
     };
     auto issue_xz = [&](int gg) {
         mbar_expect_tx(barXZ, (uint32_t)(GS * 8) * ((LOAD_X ? 1 : 0) + (LOAD_Z ? 1 : 0)));
+#ifdef DGTD_L2_HINTS
+        if (LOAD_X) bulk_load_hint(wX, (MODE == MODE_STAGE1 ? A.yin : A.x) + (size_t)gg * GS, GS * 8, barXZ, polOnce);
+        if (LOAD_Z) bulk_load_hint(wZ, A.z + (size_t)gg * GS, GS * 8, barXZ, polOnce);
+#else
         if (LOAD_X) bulk_load(wX, (MODE == MODE_STAGE1 ? A.yin : A.x) + (size_t)gg * GS, GS * 8, barXZ);
         if (LOAD_Z) bulk_load(wZ, A.z + (size_t)gg * GS, GS * 8, barXZ);
+#endif
     };
     if (tid == 0) { mbar_expect_tx(barF, (uint32_t)(B::NFR * 32 * 8)); bulk_load(sm, A.bfrag, B::NFR * 32 * 8, barF); }
     if (lane == 0 && has_work) { issue_y(g); if (LOAD_X || LOAD_Z) issue_xz(g); }
     mbar_wait(barF, 0);
 
-    for (int it = 0; g < A.ngroups; g += gstride, it++) {
+    for (int it = 0; idx < A.ngroups; idx += gstride, it++) {
         const uint32_t par = it & 1;
+        const int gnext = idx + gstride < A.ngroups ? (A.order ? A.order[idx + gstride] : idx + gstride) : -1;
         const double *ge = wGeo + e * WG_GEO;
         const double *yrec = wY + e * Np * 6;
         mbar_wait(barY, par);
@@ -251,7 +306,8 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
             nb_smem = false;
             nbase = A.halo + (size_t)(-2 - info.x) * Nfp * 6;
         }
-        if (!halo_ready && __any_sync(0xffffffffu, info.x < -1)) { p2p_wait(A.pp, lane); halo_ready = true; }
+        const int mypeer = info.x < -1 ? (code >> FI_TAB_SHIFT) & FI_TAB_MASK : -1;      // partition face: peer index (WgPlan::desc)
+        if (peers_ready != 0xffffffffu) peers_ready = p2p_wait_peers(A.pp, mypeer, peers_ready);
         double uQ[PF + 1][6];
 #pragma unroll
         for (int q = 0; q < PF; q++) load_rec_split(nbase + tab_byte(nrow, q) * 6, nb_smem, uQ[q]);
@@ -306,20 +362,18 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
             double gn[3];
 #pragma unroll
             for (int d = 0; d < 3; d++) gn[d] = j == 0 ? (ji[d] + ji[3 + d]) + ji[6 + d] : -ji[3 * (j - 1) + d];   // -grad lambda_j: outward
-            const double fs = ge[18 + j];
-            const double ifs = 1.0 / fs, ifs2 = ifs * ifs;
-            const double af = al * fs;
-            double Ah[9], Ae[9];
+            // F_E = g x dH + alpha fs (dE - n (n.dE)) = g x (dH - na x dE),  F_H = -g x (dE + na x dH)   with g = fs n, na = alpha n:
+            // one cross product with na and one 3x3 map Ah = J^-1 [g x] per field (30 FMA per face node instead of the 36 of
+            // two 3x3 maps per field; 12 instead of 18 doubles of per-face set-up; 1 / fs comes with the geometry record)
+            const double ans = al * ge[26 + j];                      // alpha / fs
+            const double na0 = ans * gn[0], na1 = ans * gn[1], na2 = ans * gn[2];
+            double Ah[9];
 #pragma unroll
             for (int a = 0; a < 3; a++) {
                 const double j0 = ji[3 * a], j1 = ji[3 * a + 1], j2 = ji[3 * a + 2];
                 Ah[3 * a + 0] = j1 * gn[2] - j2 * gn[1];
                 Ah[3 * a + 1] = j2 * gn[0] - j0 * gn[2];
                 Ah[3 * a + 2] = j0 * gn[1] - j1 * gn[0];
-                const double w = (j0 * gn[0] + j1 * gn[1] + j2 * gn[2]) * ifs2;
-                Ae[3 * a + 0] = af * (j0 - w * gn[0]);
-                Ae[3 * a + 1] = af * (j1 - w * gn[1]);
-                Ae[3 * a + 2] = af * (j2 - w * gn[2]);
             }
 #pragma unroll
             for (int s = 0; s < Nfp; s++) {
@@ -337,13 +391,18 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
 #pragma unroll
                     for (int c = 0; c < 6; c++) dU[c] += sg * inc[c];
                 }
+                double wE[3], wH[3];
+                wE[0] = fma(na2, dU[1], fma(-na1, dU[2], dU[3]));    // dH - na x dE
+                wE[1] = fma(na0, dU[2], fma(-na2, dU[0], dU[4]));
+                wE[2] = fma(na1, dU[0], fma(-na0, dU[1], dU[5]));
+                wH[0] = fma(-na2, dU[4], fma(na1, dU[5], dU[0]));    // dE + na x dH
+                wH[1] = fma(-na0, dU[5], fma(na2, dU[3], dU[1]));
+                wH[2] = fma(-na1, dU[3], fma(na0, dU[4], dU[2]));
                 double ft[6];
 #pragma unroll
                 for (int a = 0; a < 3; a++) {
-                    ft[a] = fma(Ae[3 * a + 2], dU[2], fma(Ae[3 * a + 1], dU[1], fma(Ae[3 * a], dU[0],
-                            fma(Ah[3 * a + 2], dU[5], fma(Ah[3 * a + 1], dU[4], Ah[3 * a] * dU[3])))));
-                    ft[3 + a] = fma(Ae[3 * a + 2], dU[5], fma(Ae[3 * a + 1], dU[4], fma(Ae[3 * a], dU[3],
-                                -fma(Ah[3 * a + 2], dU[2], fma(Ah[3 * a + 1], dU[1], Ah[3 * a] * dU[0])))));
+                    ft[a] = fma(Ah[3 * a + 2], wE[2], fma(Ah[3 * a + 1], wE[1], Ah[3 * a] * wE[0]));
+                    ft[3 + a] = -fma(Ah[3 * a + 2], wH[2], fma(Ah[3 * a + 1], wH[1], Ah[3 * a] * wH[0]));
                 }
                 const double *fr = sFragL + (s * NT) * 32 + lane;
 #pragma unroll
@@ -370,10 +429,9 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
         const double de = ge[23], dm = ge[24], se = ge[25];          // det/eps, det/mu, sigma/eps  (jm = J / det)
         const double ae = A.a * de, am = A.a * dm, be = A.b * de, bm = A.b * dm;
         const bool keep_y = A.has_sigma != 0;        // the conductivity term reads E of y_in in the epilogue
-        const int gnext = g + gstride;
         if (!keep_y) {
             __syncwarp();
-            if (lane == 0 && gnext < A.ngroups) issue_y(gnext);
+            if (lane == 0 && gnext >= 0) issue_y(gnext);
         }
         if (LOAD_X || LOAD_Z) mbar_wait(barXZ, par);
 #pragma unroll
@@ -425,17 +483,20 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
             }
         fence_async_smem();
         __syncwarp();
-        if (MODE != MODE_MULT && A.pp.signal_epoch != 0 && info.x < -1) {   // my traces of the new stage vector -> the peer's halo
-            const int2 hp = A.pp.hpush[-2 - info.x];
-            const uint4 prow = sTab[hp.x >> 8];
-            double *dst = A.pp.peer_out[hp.x & 0xff] + (size_t)hp.y * Nfp * 6;
-            const double *src = (MODE == MODE_STAGE4 ? wZ : wX) + e * Np * 6;
+        if (MODE != MODE_MULT && A.pp.signal_epoch != 0 && __any_sync(0xffffffffu, info.x < -1)) {
+            if (info.x < -1) {                               // my traces of the new stage vector -> the peer's halo
+                const int2 hp = A.pp.hpush[-2 - info.x];
+                const uint4 prow = sTab[hp.x >> 8];
+                double *dst = A.pp.peer_out[hp.x & 0xff] + (size_t)hp.y * Nfp * 6;
+                const double *src = (MODE == MODE_STAGE4 ? wZ : wX) + e * Np * 6;
 #pragma unroll
-            for (int m = 0; m < Nfp; m++) {
-                double r[6];
-                load_rec(src + tab_byte(prow, m) * 6, r);
-                store_rec(dst + m * 6, r);
+                for (int m = 0; m < Nfp; m++) {
+                    double r[6];
+                    load_rec(src + tab_byte(prow, m) * 6, r);
+                    store_rec(dst + m * 6, r);
+                }
             }
+            p2p_arrive(A.pp, mypeer, lane);
         }
         if (lane == 0) {
             const size_t goff = (size_t)g * GS;
@@ -443,19 +504,27 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
             if (MODE == MODE_STAGE4) bulk_store(A.yout + goff, wZ, GS * 8);
             else if (STORE_Z) bulk_store(A.z + goff, wZ, GS * 8);
             bulk_commit();
-            if (keep_y && gnext < A.ngroups) issue_y(gnext);
+            if (keep_y && gnext >= 0) issue_y(gnext);
             if (!(LOAD_X || LOAD_Z)) bulk_wait_read();            // the next epilogue writes these buffers again
         }
         __syncwarp();
+        g = gnext;
     }
     if (lane == 0) bulk_wait_all();
-    if (MODE != MODE_MULT && A.pp.signal_epoch != 0) p2p_signal(A.pp);
 }
 
 // Stand-alone producer of an exchange (the state came from the host, or Mult was called on a foreign vector): the traces of
 // `y` (aos layout) go to the peers' halo buffers, then the same last-CTA signal.
+// Flow control: exchange e overwrites the buffer the peers read exchange e-2 from.  A rank signals m only after its reads of
+// every exchange < m (stream order; a stage kernel signals at its end), so every CTA first waits for the peers' flags to
+// reach wait_epoch = e-1 before it stores anything (a rank that runs ahead of a slow neighbour must not clobber the traces
+// that neighbour is still consuming).
 __global__ void halo_push_kernel(const double *y, const long long *send_off, int nrec, int Nfp, const WgP2P pp)
 {
+    if (pp.wait_epoch != 0) {
+        if (threadIdx.x < 32) p2p_wait(pp, threadIdx.x);
+        __syncthreads();
+    }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nrec; i += gridDim.x * blockDim.x) {
         const int s = i / Nfp, m = i - s * Nfp;
         const int2 hp = pp.hpush[s];
@@ -464,6 +533,15 @@ __global__ void halo_push_kernel(const double *y, const long long *send_off, int
         store_rec(pp.peer_out[hp.x & 0xff] + ((size_t)hp.y * Nfp + m) * 6, r);
     }
     p2p_signal(pp);
+}
+
+// halo pack of the NCCL send/recv path: send[s][c] = y[send_off[s] + c]  (48-byte node records, receiver's face-node order)
+__global__ void pack_records_kernel(const double *y, const long long *send_off, int ns, double *send)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns * 3; i += gridDim.x * blockDim.x) {
+        const int s = i / 3, ch = i - 3 * s;
+        reinterpret_cast<double2 *>(send)[i] = *reinterpret_cast<const double2 *>(y + send_off[s] + 2 * ch);
+    }
 }
 
 // ---- layout conversion between the reference layout [6][Nloc] (Fields.h:45-65) and the aos device layout ---------------

@@ -83,8 +83,10 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
     __syncthreads();
 
     const int gstride = gridDim.x * B::NW, ngroups = A.ngroups * (BLK_E / WH_E);   // WgArgs counts groups of 8
-    int g = blockIdx.x * B::NW + warp;
-    bool halo_ready = A.pp.wait_epoch == 0;
+    int idx = blockIdx.x * B::NW + warp;                 // position in the processing order (units of 4 elements)
+    auto unit_at = [&](int i) { return A.order ? A.order[i >> 1] * 2 + (i & 1) : i; };      // WgPlan::order lists groups of 8
+    int g = idx < ngroups ? unit_at(idx) : idx;
+    unsigned peers_ready = A.pp.wait_epoch == 0 ? 0xffffffffu : 0u;
     const uint4 ownrow = sTab[j];
     const bool inject = A.pw_on && (A.gate == nullptr || *A.gate >= 1e-16);
     const double sgn = h ? -1.0 : 1.0;                   // u~_E = -(J/det)^T E feeds the H rows, u~_H = +(J/det)^T H the E rows
@@ -101,11 +103,12 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
         if (LOAD_Z) bulk_load(wZ, A.z + (size_t)gg * GS, GS * 8, barXZ);
     };
     if (tid == 0) { mbar_expect_tx(barF, (uint32_t)(B::NFR * 32 * 8)); bulk_load(sm, A.bfrag, B::NFR * 32 * 8, barF); }
-    if (leader && g < ngroups) { issue_y(g); if (LOAD_X || LOAD_Z) issue_xz(g); }
+    if (leader && idx < ngroups) { issue_y(g); if (LOAD_X || LOAD_Z) issue_xz(g); }
     mbar_wait(barF, 0);
 
-    for (int it = 0; g < ngroups; g += gstride, it++) {
+    for (int it = 0; idx < ngroups; idx += gstride, it++) {
         const uint32_t par = it & 1;
+        const int gnext = idx + gstride < ngroups ? unit_at(idx + gstride) : -1;
         const double *ge = wGeo + e * WG_GEO;
         const double *yrec = wY + e * Np * 6;
         mbar_wait(barY, par);
@@ -137,7 +140,8 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
             nb_smem = false;
             nbase = A.halo + (size_t)(-2 - info.x) * Nfp * 6;
         }
-        if (!halo_ready && __any_sync(0xffffffffu, info.x < -1)) { p2p_wait(A.pp, lane); halo_ready = true; }
+        const int mypeer = info.x < -1 ? (code >> FI_TAB_SHIFT) & FI_TAB_MASK : -1;      // partition face: peer index (WgPlan::desc)
+        if (peers_ready != 0xffffffffu) peers_ready = p2p_wait_peers(A.pp, mypeer, peers_ready);
         double uQ[PF + 1][6];
 #pragma unroll
         for (int q = 0; q < PF; q++) load_rec_split(nbase + tab_byte(nrow, q) * 6, nb_smem, uQ[q]);
@@ -184,21 +188,17 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
             double gn[3];
 #pragma unroll
             for (int d = 0; d < 3; d++) gn[d] = j == 0 ? (ji[d] + ji[3 + d]) + ji[6 + d] : -ji[3 * (j - 1) + d];
-            const double fs = ge[18 + j];
-            const double ifs = 1.0 / fs, ifs2 = ifs * ifs;
-            const double af = al * fs;
-            // F~_own = Ae dU_own + Ax dU_other, Ax = +J^-1 [n x] for the E rows, -J^-1 [n x] for the H rows
-            double Ax[9], Ae[9];
+            // F~_own = Ax (dU_other - (+-na) x dU_own):  F_E = g x (dH - na x dE), F_H = -g x (dE + na x dH), g = fs n, na = alpha n,
+            // Ax = +-J^-1 [g x]  (E rows +, H rows -); see kernels_wg.cuh
+            const double ans = sgn * al * ge[26 + j];               // +- alpha / fs
+            const double na0 = ans * gn[0], na1 = ans * gn[1], na2 = ans * gn[2];
+            double Ax[9];
 #pragma unroll
             for (int a = 0; a < 3; a++) {
                 const double j0 = ji[3 * a], j1 = ji[3 * a + 1], j2 = ji[3 * a + 2];
                 Ax[3 * a + 0] = sgn * (j1 * gn[2] - j2 * gn[1]);
                 Ax[3 * a + 1] = sgn * (j2 * gn[0] - j0 * gn[2]);
                 Ax[3 * a + 2] = sgn * (j0 * gn[1] - j1 * gn[0]);
-                const double w = (j0 * gn[0] + j1 * gn[1] + j2 * gn[2]) * ifs2;
-                Ae[3 * a + 0] = af * (j0 - w * gn[0]);
-                Ae[3 * a + 1] = af * (j1 - w * gn[1]);
-                Ae[3 * a + 2] = af * (j2 - w * gn[2]);
             }
 #pragma unroll
             for (int s = 0; s < Nfp; s++) {
@@ -222,11 +222,12 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
 #pragma unroll
                     for (int c = 0; c < 3; c++) { dO[c] += sg * (h ? inc[3 + c] : inc[c]); dX[c] += sg * (h ? inc[c] : inc[3 + c]); }
                 }
-                double ft[3];
+                double w[3], ft[3];
+                w[0] = fma(na2, dO[1], fma(-na1, dO[2], dX[0]));      // dU_other - (+-na) x dU_own
+                w[1] = fma(na0, dO[2], fma(-na2, dO[0], dX[1]));
+                w[2] = fma(na1, dO[0], fma(-na0, dO[1], dX[2]));
 #pragma unroll
-                for (int a = 0; a < 3; a++)
-                    ft[a] = fma(Ae[3 * a + 2], dO[2], fma(Ae[3 * a + 1], dO[1], fma(Ae[3 * a], dO[0],
-                            fma(Ax[3 * a + 2], dX[2], fma(Ax[3 * a + 1], dX[1], Ax[3 * a] * dX[0])))));
+                for (int a = 0; a < 3; a++) ft[a] = fma(Ax[3 * a + 2], w[2], fma(Ax[3 * a + 1], w[1], Ax[3 * a] * w[0]));
                 const double *fr = sFragL + (s * NT) * 32 + lane;
 #pragma unroll
                 for (int nt = 0; nt < NT - 1; nt++) {
@@ -249,10 +250,9 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
         const double dmat = h ? ge[24] : ge[23];            // det/mu : det/eps
         const double se = h ? 0.0 : ge[25];                 // sigma/eps acts on E only
         const bool keep_y = A.has_sigma != 0;
-        const int gnext = g + gstride;
         if (!keep_y) {
             __syncwarp();                                   // every lane has read y_in for the last time
-            if (leader && gnext < ngroups) issue_y(gnext);
+            if (leader && gnext >= 0) issue_y(gnext);
         }
         if (LOAD_X || LOAD_Z) mbar_wait(barXZ, par);
         const bool plain = keep_y || MODE == MODE_MULT;
@@ -297,8 +297,8 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
             }
         fence_async_smem();
         __syncwarp();                                       // complete records in wX / wZ
-        if (h == 0) {
-            if (MODE != MODE_MULT && A.pp.signal_epoch != 0 && info.x < -1) {
+        if (MODE != MODE_MULT && A.pp.signal_epoch != 0 && __any_sync(0xffffffffu, info.x < -1)) {
+            if (h == 0 && info.x < -1) {                     // the E-row lane of (element, face) ships the whole records
                 const int2 hp = A.pp.hpush[-2 - info.x];
                 const uint4 prow = sTab[hp.x >> 8];
                 double *dst = A.pp.peer_out[hp.x & 0xff] + (size_t)hp.y * Nfp * 6;
@@ -310,20 +310,21 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
                     store_rec(dst + m * 6, r);
                 }
             }
-            if (lane == 0) {
-                const size_t goff = (size_t)g * GS;
-                if (STORE_X) bulk_store(A.yout + goff, wX, GS * 8);
-                if (MODE == MODE_STAGE4) bulk_store(A.yout + goff, wZ, GS * 8);
-                else if (STORE_Z) bulk_store(A.z + goff, wZ, GS * 8);
-                bulk_commit();
-                if (keep_y && gnext < ngroups) issue_y(gnext);
-                if (!(LOAD_X || LOAD_Z)) bulk_wait_read();
-            }
+            p2p_arrive(A.pp, h == 0 ? mypeer : -1, lane);
+        }
+        if (lane == 0) {
+            const size_t goff = (size_t)g * GS;
+            if (STORE_X) bulk_store(A.yout + goff, wX, GS * 8);
+            if (MODE == MODE_STAGE4) bulk_store(A.yout + goff, wZ, GS * 8);
+            else if (STORE_Z) bulk_store(A.z + goff, wZ, GS * 8);
+            bulk_commit();
+            if (keep_y && gnext >= 0) issue_y(gnext);
+            if (!(LOAD_X || LOAD_Z)) bulk_wait_read();
         }
         __syncwarp();
+        g = gnext;
     }
     if (leader) bulk_wait_all();
-    if (MODE != MODE_MULT && A.pp.signal_epoch != 0) p2p_signal(A.pp);
 }
 
 }  // namespace dgtd

@@ -1,12 +1,13 @@
 // Simplex meshes on the host: readers for the two formats the reference's cases use
 // (Gmsh 2.2 ASCII as read by mfem::Mesh::LoadFromFile, src/driver/driver.cpp:1176-1183, and "MFEM mesh v1.0"),
-// a Cartesian tetrahedral box generator (config 5: Mesh::MakeCartesian3D(n,n,n,TETRAHEDRON)) and a
-// coordinate-bisection partitioner standing in for METIS (Mesh::GeneratePartitioning, driver.cpp:1269;
-// METIS is not available in the image — same int[NE] contract).
+// a Cartesian tetrahedral box generator (config 5: Mesh::MakeCartesian3D(n,n,n,TETRAHEDRON)) and the two partitioners
+// behind the reference's int[NE] contract (Mesh::GeneratePartitioning, driver.cpp:1269): recursive coordinate bisection
+// and METIS k-way on the element dual graph (the static METIS shipped inside the CUDA toolkit).
 #include "host.hpp"
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <fstream>
 #include <map>
 #include <numeric>
@@ -27,7 +28,7 @@ static double det_of(const Mesh &m, int e)
            J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
 }
 
-void Mesh::validate_and_orient()
+void Mesh::validate_and_orient(bool reorient)
 {
     if (dim < 1 || dim > 3) throw Error(-3, "mesh dimension must be 1, 2 or 3");
     if (verts.size() % 3) throw Error(-3, "vertex array must hold 3 doubles per vertex");
@@ -40,6 +41,9 @@ void Mesh::validate_and_orient()
         if (d == 0.0 || !std::isfinite(d)) throw Error(-3, "degenerate element " + std::to_string(e));
         if (d < 0.0) {
             if (dim == 1) throw Error(-3, "inverted segment " + std::to_string(e));
+            // caller-owned numbering (dgtd_mesh_from_arrays): a silent swap would permute this element's dofs relative to the
+            // caller's FE space, so it is an error there; the file loaders and generators own their numbering
+            if (!reorient) throw Error(-3, "inverted element " + std::to_string(e) + " (negative Jacobian): orient the mesh first, as mfem::Mesh does on load");
             std::swap(elems[(size_t)e * (dim + 1)], elems[(size_t)e * (dim + 1) + 1]);
         }
     }
@@ -259,6 +263,13 @@ std::vector<int> partition_metis(const Mesh &m, int nranks)
     for (int e = 0; e < ne; e++) { adjncy.insert(adjncy.end(), adj[e].begin(), adj[e].end()); xadj[e + 1] = (long long)adjncy.size(); }
     long long nv = ne, ncon = 1, np = nranks, cut = 0, options[40];
     METIS_SetDefaultOptions(options);
+    // load imbalance is lost time on ranks that run in lock step: ask for 0.2 % (METIS' default tolerance is 3 %, which
+    // the reference inherits, mesh.cpp:8378); DGTD_B200_METIS_UFACTOR overrides (30 = the reference's behaviour)
+    {
+        const char *uf = std::getenv("DGTD_B200_METIS_UFACTOR");
+        options[16 /* METIS_OPTION_UFACTOR */] = uf ? std::atoll(uf) : 2;
+        options[11 /* METIS_OPTION_CONTIG */] = 1;
+    }
     std::vector<long long> p64(ne, 0);
     const int rc = METIS_PartGraphKway(&nv, &ncon, xadj.data(), adjncy.data(), nullptr, nullptr, nullptr, &np, nullptr, nullptr, options, &cut, p64.data());
     if (rc != 1) throw Error(-1, "METIS_PartGraphKway failed (" + std::to_string(rc) + ")");

@@ -97,13 +97,14 @@ WgPlan build_wg_plan(const HostOp &H)
         double *g = &W.geo[(size_t)e * WG_GEO];
         if (e < NE) {
             const double *v1 = &H.geo[(size_t)e * GEO_STRIDE], *jc = &H.jac[(size_t)e * 10];
-            // J / det J (covariant transform and push-forward share it), J^-1, fscale, 1/det, det/eps, det/mu, sigma/eps
+            // J / det J (covariant transform and push-forward share it), J^-1, fscale, 1/det, det/eps, det/mu, sigma/eps, 1/fscale
             for (int i = 0; i < 9; i++) { g[i] = jc[i] / jc[9]; g[9 + i] = v1[i]; }
             for (int f = 0; f < 4; f++) g[18 + f] = v1[9 + f];
             g[22] = 1.0 / jc[9]; g[23] = jc[9] * v1[13]; g[24] = jc[9] * v1[14]; g[25] = v1[15];
+            for (int f = 0; f < 4; f++) g[26 + f] = 1.0 / v1[9 + f];
         } else {   // padding element: unit geometry, vacuum; its state stays zero
             g[0] = g[4] = g[8] = 1.0; g[9] = g[13] = g[17] = 1.0;
-            g[18] = g[19] = g[20] = g[21] = 1.0; g[22] = g[23] = g[24] = 1.0;
+            g[18] = g[19] = g[20] = g[21] = 1.0; g[22] = g[23] = g[24] = 1.0; g[26] = g[27] = g[28] = g[29] = 1.0;
         }
     }
 
@@ -131,6 +132,9 @@ WgPlan build_wg_plan(const HostOp &H)
     };
 
     // ---- face descriptors ---------------------------------------------------------------------------------------------------
+    std::vector<int> peer_of_slot((size_t)H.n_halo_faces, 0);
+    for (size_t pi = 0; pi < H.peers.size(); pi++)
+        for (int s = H.peers[pi].recv_off; s < H.peers[pi].recv_off + H.peers[pi].nfaces; s++) peer_of_slot[(size_t)s] = (int)pi;
     W.desc.assign((size_t)W.NEpad * 8, 0);
     for (int e = 0; e < W.NEpad; e++)
         for (int f = 0; f < 4; f++) {
@@ -139,7 +143,9 @@ WgPlan build_wg_plan(const HostOp &H)
             const int nb = H.finfo[((size_t)e * 4 + f) * 2];
             int code = H.finfo[((size_t)e * 4 + f) * 2 + 1];
             const int old = (code >> FI_TAB_SHIFT) & FI_TAB_MASK;
-            int row = nb >= 0 ? nbr_row(f, old) : nb == -1 ? f : 4 + f;
+            // interior face: row of the neighbour's node table; boundary: own row; partition face: the table is always row
+            // 4 + f (canonical order of the halo slot), so the field carries the PEER INDEX the consumer waits for
+            int row = nb >= 0 ? nbr_row(f, old) : nb == -1 ? f : peer_of_slot[-2 - nb];
             if (row > FI_TAB_MASK) throw Error(DGTD_ERR_UNSUPPORTED, "too many distinct face orientations");
             code = (code & ~(FI_TAB_MASK << FI_TAB_SHIFT)) | (row << FI_TAB_SHIFT);
             fo[0] = nb; fo[1] = code;
@@ -192,6 +198,32 @@ WgPlan build_wg_plan(const HostOp &H)
                 W.hpush[(size_t)s * 2 + 1] = pp.remote_off + (s - pp.send_off);
             }
         }
+    }
+    // ---- processing order and per-peer push counts of the fused halo exchange -------------------------------------------------
+    // Units (groups of 8 elements; the half-row kernel works on their halves) that own a partition face come FIRST in a
+    // launch: their traces reach the neighbours while the interior is still being computed, and the flag of a peer is
+    // raised by whichever warp stores the last of the `need` units that push to it (kernels_wg.cuh: p2p_arrive).
+    W.order.resize((size_t)W.ngroups);
+    W.need8.assign(H.peers.size(), 0); W.need4.assign(H.peers.size(), 0);
+    {
+        std::vector<char> front((size_t)W.ngroups, 0);
+        for (int u = 0; u < 2 * W.ngroups; u++) {            // u = unit of 4 elements
+            unsigned mask = 0;
+            for (int e = 4 * u; e < std::min(4 * u + 4, NE); e++)
+                for (int f = 0; f < 4; f++) { const int nb = W.desc[((size_t)e * 4 + f) * 2]; if (nb < -1) mask |= 1u << peer_of_slot[-2 - nb]; }
+            for (size_t pi = 0; pi < H.peers.size(); pi++) if (mask >> pi & 1) W.need4[pi]++;
+            if (mask) front[(size_t)(u >> 1)] = 1;
+        }
+        for (int g = 0; g < W.ngroups; g++) {
+            unsigned mask = 0;
+            for (int e = 8 * g; e < std::min(8 * g + 8, NE); e++)
+                for (int f = 0; f < 4; f++) { const int nb = W.desc[((size_t)e * 4 + f) * 2]; if (nb < -1) mask |= 1u << peer_of_slot[-2 - nb]; }
+            for (size_t pi = 0; pi < H.peers.size(); pi++) if (mask >> pi & 1) W.need8[pi]++;
+        }
+        int k = 0;
+        for (int g = 0; g < W.ngroups; g++) if (front[(size_t)g]) W.order[(size_t)k++] = g;
+        W.nfront = k;
+        for (int g = 0; g < W.ngroups; g++) if (!front[(size_t)g]) W.order[(size_t)k++] = g;
     }
     // ---- halo pack list ---------------------------------------------------------------------------------------------------
     W.send_off.resize(H.send_node.size());

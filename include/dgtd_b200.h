@@ -79,7 +79,8 @@ typedef struct dgtd_options {
 
 /* ---- mesh (host) ---------------------------------------------------------------------------- */
 /* verts: nv*3 doubles (unused coordinates 0); elems: ne*(dim+1) vertex ids in the host code's
- * element-local order (mfem::Mesh::GetElementVertices); bdr: nbe*dim vertex ids.                  */
+ * element-local order (mfem::Mesh::GetElementVertices); bdr: nbe*dim vertex ids.  Elements must be positively oriented
+ * (mfem::Mesh orients on load): an inverted element fails with DGTD_ERR_MESH instead of being silently renumbered. */
 int  dgtd_mesh_from_arrays(int dim, int nv, const double *verts, int ne, const int *elems,
                            const int *elem_attr, int nbe, const int *bdr, const int *bdr_attr,
                            dgtd_mesh **out);
@@ -123,9 +124,10 @@ int  dgtd_get_state(dgtd_ctx *, double *host_6N);
 /* the same with LOCAL host vectors [6][n_local] in this rank's element order (dgtd_local_elements)  */
 int  dgtd_set_state_local(dgtd_ctx *, const double *host_6nlocal);
 int  dgtd_get_state_local(dgtd_ctx *, double *host_6nlocal);
-/* device-resident state of this rank in the kernels' NATIVE layout: tetrahedra of order <= 4 use the blocked layout
- * (groups of 8 local elements, [node][element in group][6 components], padded to whole groups); everything else
- * [6][n_local].  Use dgtd_get_state_local / dgtd_mult(on_device=1) for layout-independent access.               */
+/* device-resident state of this rank in the kernels' NATIVE layout: tetrahedra of order <= 4 use the "aos" layout
+ * offset(e, n, c) = (e * Np + n) * 6 + c over local elements in Morton order, n = device node id ("wg_dev2ref" of
+ * dgtd_setup_query maps it to the reference node), padded to whole groups of 8 elements; everything else [6][n_local].
+ * Use dgtd_get_state_local / dgtd_mult(on_device=1) for layout-independent access.                                */
 int  dgtd_state_device_ptr(dgtd_ctx *, double **dev);
 
 /* TimeDependentOperator::Mult at time t (SetTime + Mult).  Host pointers: global [6N] vectors,
@@ -160,6 +162,7 @@ int  dgtd_gather_create(dgtd_ctx *, long long n, const long long *dofs, dgtd_gat
 int  dgtd_gather_dofs(const dgtd_gather *, long long *dofs_local);
 int  dgtd_gather_launch(dgtd_ctx *, dgtd_gather *, double *host_out);
 int  dgtd_gather_wait(dgtd_ctx *, dgtd_gather *);
+/* either order of dgtd_gather_destroy and dgtd_destroy is fine: a gather whose context is gone only frees its host shell */
 void dgtd_gather_destroy(dgtd_gather *);
 /* Host-only helper for surface exports: the (global element, local face) pairs lying on boundary elements with one of
  * the given attributes — NearToFarFieldSubMesher's selection (SubMesher.cpp:832-905) keeps one element per face; here
@@ -176,7 +179,8 @@ int  dgtd_kernel_info(const dgtd_ctx *, char *buf, int cap);
  * Replaces the six blocking MPI neighbour exchanges of GlobalEvolution::Mult (GlobalEvolution.cpp:763-774).
  * dgtd_comm_init is collective: NCCL bootstrap, then (tetrahedra, order <= 4) every rank maps its neighbours' halo
  * buffers with CUDA IPC; from then on the stage kernel itself stores the traces of its partition faces into the
- * neighbour's buffer and only the warps owning such a face wait for the neighbour's epoch flag (no pack kernel, no
+ * neighbour's buffer (partition-face groups first in a launch, a neighbour's flag raised as soon as the last group touching
+ * it has stored) and only the lanes owning such a face wait for that neighbour's epoch flag (no pack kernel, no
  * collective on the path).  If IPC is unavailable on any rank, all ranks use ncclSend/ncclRecv instead.
  * dgtd_destroy of a multi-rank context is collective too (neighbours must stop storing before a buffer is freed).
  * Like the reference's MPI calls, every entry point that evaluates the operator or replaces the state (dgtd_mult,
@@ -193,8 +197,9 @@ int  dgtd_halo_bytes(const dgtd_ctx *, long long *bytes);
 
 /* Host-only diagnostic (no CUDA, no compute): copies one of the flat tables a rank would upload — "dims", "D", "lift",
  * "nodes", "fnodes", "geo", "finfo", "ftab", "elem_gid", "tfsf_xyz", "gate_xyz", "tfsf_side", "send_node", "peers", "peers5",
- * "node_coords", the plan of the warp-per-group kernel "wg_dims", "wg_bfrag", "wg_geo", "wg_forder", "wg_hpush", "wg_tab", "wg_desc", "wg_send_off", "wg_dev2ref", and for tetrahedra the plan of the tensor-core kernel "blk_dims", "blk_geo", "blk_desc", "blk_afrag",
- * "blk_send_off" — so that tests can check the setup against the oracle without a GPU.                            */
+ * "node_coords", the plan of the warp-per-group kernel "wg_dims", "wg_bfrag", "wg_geo", "wg_forder", "wg_hpush", "wg_tab", "wg_desc", "wg_send_off", "wg_dev2ref", "wg_order",
+ * "wg_need" (per peer: groups of 8 and of 4 elements pushing to it, then the number of front groups)
+ * — so that tests can check the setup against the oracle without a GPU.                            */
 int  dgtd_setup_query(const dgtd_mesh *, const dgtd_options *, const char *name, void *buf, long long cap_bytes, long long *size_bytes);
 
 const char *dgtd_last_error(void);

@@ -797,6 +797,26 @@ static int cmdGen(std::map<std::string, std::string> &a, bool bench)
          for (int q : snaps) if (q == s) { dump(out + "/x_step" + std::to_string(s) + ".f64", x.GetData(), (size_t)6 * N); }
    }
    double tRun = now() - tr0;
+   // median of `repeats` timed windows of `steps` RK4 steps each, and the share of the window spent in the
+   // operator application alone (4 SparseMatrix::Mult per step, sparsemat.cpp:921-931) against the 7 AXPY passes of RK4Solver
+   const int repeats = bench && a.count("repeats") ? std::max(1, std::stoi(a["repeats"])) : 1;
+   std::vector<double> runs{tRun};
+   for (int r = 1; r < repeats; r++)
+   {
+      double q0 = now();
+      for (int s = 0; s < steps; s++) { double d = dt; rk.Step(x, t, d); }
+      runs.push_back(now() - q0);
+   }
+   std::vector<double> sorted = runs; std::sort(sorted.begin(), sorted.end());
+   const double tMed = sorted[sorted.size() / 2];
+   double tSpmv = 0.0;
+   if (bench && a.count("spmv-share"))
+   {
+      Vector k(6 * N); op.SetTime(t);
+      double q0 = now();
+      for (int s = 0; s < 4 * steps; s++) { op.Mult(x, k); }
+      tSpmv = now() - q0;
+   }
    if (!out.empty()) { dump(out + "/x_final.f64", x.GetData(), (size_t)6 * N); }
 
    int threads = 1;
@@ -816,8 +836,10 @@ static int cmdGen(std::map<std::string, std::string> &a, bool bench)
       << ", \"pw\": {\"on\": " << (pd.pw.on ? "true" : "false") << ", \"spread\": " << pd.pw.spread << ", \"mean1d\": " << pd.pw.mean1d
       << ", \"freq\": " << pd.pw.freq << ", \"pol\": [" << pd.pw.pol[0] << ", " << pd.pw.pol[1] << ", " << pd.pw.pol[2]
       << "], \"dir\": [" << pd.pw.dir[0] << ", " << pd.pw.dir[1] << ", " << pd.pw.dir[2] << "]}"
-      << ", \"assemble_s\": " << tAsm << ", \"run_s\": " << tRun << ", \"threads\": " << threads
-      << ", \"dof_updates_per_s\": " << (tRun > 0 ? 6.0 * N * 4.0 * steps / tRun : 0.0) << "}";
+      << ", \"assemble_s\": " << tAsm << ", \"run_s\": " << tMed << ", \"threads\": " << threads << ", \"repeats\": " << repeats << ", \"runs_s\": [";
+   for (size_t r = 0; r < runs.size(); r++) { js << (r ? ", " : "") << runs[r]; }
+   js << "], \"spmv_s\": " << tSpmv << ", \"spmv_share\": " << (tMed > 0 ? tSpmv / tMed : 0.0)
+      << ", \"dof_updates_per_s\": " << (tMed > 0 ? 6.0 * N * 4.0 * steps / tMed : 0.0) << "}";
    std::cout << js.str() << std::endl;
    if (!out.empty()) { std::ofstream f(out + "/meta.json"); f << js.str() << "\n"; }
    return 0;

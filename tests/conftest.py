@@ -25,10 +25,7 @@ def config_cases():
     return sorted(os.path.basename(p)[:-len(".cfg.npz")] for p in glob.glob(os.path.join(GOLDEN, "*.cfg.npz")))
 
 
-def smooth_state(xyz):
-    """`--init smooth` of oracle/ref/dgtd_ref.cpp: u_c = sin(1.3 x + 0.7 c + 0.2) cos(0.9 y - 0.4 c) + 0.5 sin(1.1 z + c)."""
-    x, y, z = xyz[:, 0], xyz[:, 1], xyz[:, 2]
-    return np.concatenate([np.sin(1.3 * x + 0.7 * c + 0.2) * np.cos(0.9 * y - 0.4 * c) + 0.5 * np.sin(1.1 * z + c) for c in range(6)])
+from golden_io import initial_state, smooth_state  # noqa: E402,F401  (oracle-free fixture helpers, shared with bench.py)
 
 
 def load_config_case(name):
@@ -46,20 +43,6 @@ def load_config_case(name):
         w = meta["pw"]
         pb.planewave = PlaneWave(w["spread"], w["mean1d"], w["pol"], w["dir"], w["freq"])
     return pb, meta, {k: z[k] for k in ("x0_sample_f64", "k0_sample_f64", "x_final_sample_f64")}
-
-
-def initial_state(meta, xyz):
-    """The fixture's initial condition, rebuilt from node coordinates [N][3]."""
-    if meta["init"] == "smooth":
-        return smooth_state(xyz)
-    kind, comp, modes = meta["init"].split(":")
-    assert kind == "resonant"
-    x0 = np.zeros((6, len(xyz)))
-    v = np.ones(len(xyz))
-    for k, m in enumerate(modes.split(",")):
-        v = v * np.sin(float(m) * np.pi * xyz[:, k])
-    x0[int(comp)] = v
-    return x0.ravel()
 
 
 def load_golden(name):

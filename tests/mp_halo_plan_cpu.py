@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """World-size-2 gloo worker (CPU): each rank builds its own partition's halo plan through the C ABI's host-side query,
 ships the coordinates of the nodes it would send, and checks that what arrives is exactly its own face nodes in its
-own face-node order — for the trace layout of both kernels (reference layout and blocked layout offsets)."""
+own face-node order — for the trace layout of both kernel families (reference layout and aos record offsets)."""
 import os
 import sys
 
@@ -29,11 +29,12 @@ def main():
         Np, Nfp = O.Np, O.Nfp
         gid = q("elem_gid", np.int32)
         send = q("send_node", np.int32)
-        soff = q("blk_send_off", np.int64)
+        soff = q("wg_send_off", np.int64)
+        r2d = np.argsort(q("wg_dev2ref", np.int32))
         finfo = q("finfo", np.int32).reshape(len(gid), 4, 2)
-        # blocked offsets address the same nodes as the reference-layout send list
+        # aos record offsets address the same nodes as the reference-layout send list
         le, node = send // Np, send % Np
-        assert np.array_equal(soff, (((le >> 3) * Np + node) * 8 + (le & 7)) * 6)
+        assert np.array_equal(soff, (le * Np + r2d[node]) * 6)
         xyz = O.xyz.reshape(-1, 3)
         mine = torch.from_numpy(xyz[gid[le] * Np + node].copy())
         other = torch.zeros_like(mine)

@@ -76,57 +76,31 @@ def test_setup_tables_match_the_oracle(name):
 
 
 @pytest.mark.parametrize("name", [n for n in golden_cases() if "3d" in n])
-def test_tensor_core_plan_is_consistent(name):
-    """The blocked plan re-expresses finfo per batch (in-batch neighbour / boundary / trace slot): decode it back."""
+def test_wg_plan_records_are_consistent(name):
+    """The warp-per-group plan keeps HostOp's face descriptors (padding elements: boundary, no condition), its geometry
+    records satisfy (J/det) det Jinv = I, and its node tables are permutations of the face nodes."""
     pb, _ = load_golden(name)
     O = HesthavenOracle(pb)
     mesh, kw = product_mesh_and_kwargs(pb)
     Np, Nfp, NE = O.Np, O.Nfp, O.NE
-    G, ngroups, nbatch, NEpad, slots, MT, KSV, KSL, DS = (int(v) for v in _q(mesh, kw, "blk_dims", np.int32))
-    assert NEpad % 8 == 0 and NEpad >= NE and nbatch * 8 * G == NEpad and DS % 4 == 0
+    ngroups, NEpad, NT, KSV, nfv, nfl, ntab, GEO = (int(v) for v in _q(mesh, kw, "wg_dims", np.int32))
+    assert NEpad == 8 * ngroups >= NE and NT == (Np + 7) // 8 and KSV == (Np + 3) // 4
     finfo = _q(mesh, kw, "finfo", np.int32).reshape(NE, 4, 2)
-    desc = _q(mesh, kw, "blk_desc", np.int32).reshape(nbatch, DS)
-    EB = 8 * G
-    for b in range(nbatch):
-        fi = desc[b, :EB * 8].reshape(EB, 4, 2)
-        td = desc[b, EB * 8:EB * 8 + slots * 2].reshape(slots, 2)
-        used = desc[b, EB * 8 + slots * 2]
-        seen = set()
-        for le in range(EB):
-            e = b * EB + le
-            for f in range(4):
-                x, code = fi[le, f]
-                if e >= NE:
-                    assert x == -1 and (code & 0xf) == 0
-                    continue
-                nb, code1 = finfo[e, f]
-                assert code == code1
-                if nb == -1:
-                    assert x == -1
-                elif x >= 0:
-                    assert b * EB + x == nb
-                else:
-                    s = -2 - x
-                    assert 0 <= s < used and s not in seen
-                    seen.add(s)
-                    assert td[s, 0] == nb and td[s, 1] == FI_TAB(code)
-        assert len(seen) == used
-    # geometry records: J * Jinv = I, 1/det
-    geo = _q(mesh, kw, "blk_geo", np.float64).reshape(NEpad, 32)
-    J, Ji = geo[:, :9].reshape(-1, 3, 3), geo[:, 9:18].reshape(-1, 3, 3)
-    assert np.abs(np.einsum("eda,eac->edc", J, Ji) - np.eye(3)).max() < 1e-12
-    assert np.allclose(geo[:NE, 22] * np.linalg.det(J[:NE]), 1.0, rtol=1e-13)
-    # A fragments reproduce D and LIFT/2 (lane l holds A[l>>2][l&3])
-    af = _q(mesh, kw, "blk_afrag", np.float64)
-    Dm = _q(mesh, kw, "D", np.float64).reshape(3, Np, Np)
-    L = _q(mesh, kw, "lift", np.float64).reshape(4, Np, Nfp)
-    Lfull = np.concatenate([L[f] for f in range(4)], axis=1)      # (Np, 4*Nfp)
-    av = af[:3 * MT * KSV * 32].reshape(3, MT, KSV, 8, 4)
-    al = af[3 * MT * KSV * 32:].reshape(MT, KSL, 8, 4)
-    Dr = np.zeros((3, MT * 8, KSV * 4)); Dr[:, :Np, :Np] = Dm
-    Lr = np.zeros((MT * 8, KSL * 4)); Lr[:Np, :4 * Nfp] = 0.5 * Lfull
-    assert np.array_equal(av.transpose(0, 1, 3, 2, 4).reshape(3, MT * 8, KSV * 4), Dr)
-    assert np.array_equal(al.transpose(0, 2, 1, 3).reshape(MT * 8, KSL * 4), Lr)
+    desc = _q(mesh, kw, "wg_desc", np.int32).reshape(NEpad, 4, 2)
+    assert np.array_equal(desc[:NE, :, 0], finfo[:, :, 0])
+    assert np.array_equal(desc[:NE, :, 1] & 0xf, finfo[:, :, 1] & 0xf) and np.array_equal(desc[:NE, :, 1] >> 12, finfo[:, :, 1] >> 12)
+    assert (desc[NE:, :, 0] == -1).all() and (desc[NE:, :, 1] == 0).all()
+    geo = _q(mesh, kw, "wg_geo", np.float64).reshape(NEpad, GEO)
+    Jd, Ji = geo[:, :9].reshape(-1, 3, 3), geo[:, 9:18].reshape(-1, 3, 3)
+    det = 1.0 / geo[:, 22]
+    assert np.abs(np.einsum("eda,eac->edc", Jd * det[:, None, None], Ji) - np.eye(3)).max() < 1e-12
+    assert np.allclose(np.linalg.det(Jd[:NE] * det[:NE, None, None]), det[:NE], rtol=1e-12)
+    tab = _q(mesh, kw, "wg_tab", np.uint8).reshape(ntab, 16)
+    d2r = _q(mesh, kw, "wg_dev2ref", np.int32)
+    fn = _q(mesh, kw, "fnodes", np.int32).reshape(4, Nfp)
+    for f in range(4):
+        assert sorted(d2r[tab[f, :Nfp]]) == sorted(fn[f])
+        assert sorted(tab[4 + f, :Nfp]) == list(range(Nfp))
 
 
 def test_partitioner_and_halo_plan_two_ranks_in_process():

@@ -1,6 +1,6 @@
 """CPU replay of the warp-per-group stage kernel from its PLAN (dgtd_b200/csrc/wgplan.cpp): the operator B-fragments, the
 face-step tables, the descriptors, the geometry records and the device node numbering are read through dgtd_setup_query and
-interpreted in numpy exactly as kernels_wg.cuh does (DMMA tiles incl. the mixed last tile, 6x6 per-face flux map, LIFT with
+interpreted in numpy exactly as kernels_wg.cuh does (DMMA tiles incl. the mixed last tile, per-face flux map g x (dH - alpha n x dE), LIFT with
 K = 4 faces per step, push-forward with J / det), then compared with the oracle's Mult.  This pins the plan — including
 non-trivial node numberings and face-step orders — without a GPU; the GPU parity tests pin the kernel that consumes it."""
 import numpy as np
@@ -18,7 +18,8 @@ def _plan(mesh, kw, **extra):
                 bfrag=q("wg_bfrag", np.float64).reshape(-1, 32), geo=q("wg_geo", np.float64).reshape(NEpad, GEO),
                 desc=q("wg_desc", np.int32).reshape(NEpad, 4, 2), tab=q("wg_tab", np.uint8).reshape(-1, 16),
                 d2r=q("wg_dev2ref", np.int32), gid=q("elem_gid", np.int32), dims=q("dims", np.int32),
-                hpush=q("wg_hpush", np.int32).reshape(-1, 2), peers=q("peers5", np.int32).reshape(-1, 5))
+                hpush=q("wg_hpush", np.int32).reshape(-1, 2), peers=q("peers5", np.int32).reshape(-1, 5),
+                order=q("wg_order", np.int32), need=q("wg_need", np.int32), ngroups=ngroups)
 
 
 def _frag_matrix(f):
@@ -108,17 +109,17 @@ def replay_mult(P, x_ref, alpha, halo=None):
                 nrow, ne_ = tab[j], e
             Jim = Ji.reshape(3, 3)                       # [a][d]
             gn = (Jim[0] + Jim[1] + Jim[2]) if j == 0 else -Jim[j - 1]
-            af = al * fs[j]
             cross = np.array([[0, -gn[2], gn[1]], [gn[2], 0, -gn[0]], [-gn[1], gn[0], 0]])
-            Ah = Jim @ cross
-            Ae = af * (Jim - np.outer(Jim @ gn, gn) / fs[j] ** 2)
+            Ah = Jim @ cross                             # J^-1 [g x], g = fs n
+            na = al * g[26 + j] * gn                     # alpha n  (1 / fs comes with the geometry record)
+            assert abs(g[26 + j] * fs[j] - 1.0) < 1e-14
             for s in range(Nfp):
                 uM = U[e, tab[j][s]]
                 uP = trace[nrow[s]] if trace is not None else U[ne_, nrow[s]]
                 dE = uP[:3] - (1.0 - ce) * uM[:3]
                 dH = uP[3:] - (1.0 - ch) * uM[3:]
-                ft[s, j, :3] = Ah @ dH + Ae @ dE
-                ft[s, j, 3:] = -Ah @ dE + Ae @ dH
+                ft[s, j, :3] = Ah @ (dH - np.cross(na, dE))      # g x (dH - alpha n x dE)
+                ft[s, j, 3:] = -(Ah @ (dE + np.cross(na, dH)))
         for s in range(Nfp):
             for nt in range(NT - 1):
                 B = fragL[s * NT + nt]
@@ -189,6 +190,21 @@ def test_partitioned_plan_replay_with_pushed_traces(name, world, method):
     out = np.zeros(6 * O.N)
     owned = np.zeros(O.N, int)
     for r, P in enumerate(plans):
+        # fused-exchange tables: a partition face names its peer in the descriptor, the groups owning such faces come first in
+        # the processing order, and need[peer] counts the groups (of 8 / of 4 elements) that store traces to that peer
+        NE, npeers, ng = P["dims"][5], len(P["peers"]), P["ngroups"]
+        d = P["desc"]
+        for e in range(NE):
+            for f in range(4):
+                if d[e, f, 0] < -1:
+                    assert (d[e, f, 1] >> 4) & 0xff == P["hpush"][-2 - d[e, f, 0], 0] & 0xff
+        has = [sorted({int((d[e, f, 1] >> 4) & 0xff) for e in range(8 * g_, min(8 * g_ + 8, NE)) for f in range(4) if d[e, f, 0] < -1}) for g_ in range(ng)]
+        has4 = [sorted({int((d[e, f, 1] >> 4) & 0xff) for e in range(4 * u, min(4 * u + 4, NE)) for f in range(4) if d[e, f, 0] < -1}) for u in range(2 * ng)]
+        nfront = int(P["need"][-1])
+        assert sorted(P["order"].tolist()) == list(range(ng))
+        assert all(has[g_] for g_ in P["order"][:nfront]) and not any(has[g_] for g_ in P["order"][nfront:])
+        assert P["need"][:npeers].tolist() == [sum(p in h for h in has) for p in range(npeers)]
+        assert P["need"][npeers:2 * npeers].tolist() == [sum(p in h for h in has4) for p in range(npeers)]
         n_halo = sum(1 for e in range(P["dims"][5]) for f in range(4) if P["desc"][e, f, 0] < -1)
         assert sorted(halos[r]) == list(range(n_halo)), "every halo slot of a rank is written exactly by its neighbours"
         k = replay_mult(P, x, pb.alpha, halos[r]).reshape(6, -1)
