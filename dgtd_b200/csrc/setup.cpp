@@ -193,8 +193,18 @@ HostOp build_host_op(const Mesh &m, const Options &o)
         }
         auto bc = bcOf.find(attr);
         if (bc == bcOf.end()) continue;
-        if (interior) throw Error(DGTD_ERR_UNSUPPORTED, "interior PEC/PMC/SMA boundaries are not supported yet (attribute " + std::to_string(attr) + ")");
         faceBC[(size_t)it->e * nf + it->f] = bc->second;
+        if (interior) {
+            // PEC/PMC/SMA sheet inside the mesh, `global` semantics: the regular interior flux skips the face (ignore marker,
+            // DGOperatorFactory.h:373-389) and each side gets the self block of a true boundary face with the same
+            // coefficients (MaxwellDGInteriorJumpIntegrator, DGOperatorFactory.h:575-675, BilinearIntegrators.cpp:356-412):
+            // the two elements are disconnected here and both faces become boundary faces with this condition.
+            // (`hesthaven` halves the coefficients instead, HesthavenEvolution.cpp:308-310; the default operator is followed.)
+            const int e2 = nbrE[(size_t)it->e * nf + it->f], f2 = nbrF[(size_t)it->e * nf + it->f];
+            faceBC[(size_t)e2 * nf + f2] = bc->second;
+            nbrE[(size_t)it->e * nf + it->f] = nbrF[(size_t)it->e * nf + it->f] = -1;
+            nbrE[(size_t)e2 * nf + f2] = nbrF[(size_t)e2 * nf + f2] = -1;
+        }
     }
     // ---- TF/SF sides (SubMesher.cpp:677-771) ---------------------------------------------------------------
     std::vector<int> side(NE, 0), faceTF((size_t)NE * nf, 0);

@@ -298,7 +298,11 @@ class HesthavenOracle:
             for s, (e, f) in enumerate(sides):
                 vmapM[e, f] = e * Np + ref.fnodes[f]
                 face_tag[e, f] = tag
-                if len(sides) == 1:
+                # a PEC/PMC/SMA tag on an INTERIOR face: the `global` operator skips the regular interior flux there
+                # (ignore marker, DGOperatorFactory.h:373-389, bilinearform.cpp:634-690 of the fork) and assembles only the
+                # two self blocks with the true-boundary coefficients (MaxwellDGInteriorJumpIntegrator, :575-675;
+                # BilinearIntegrators.cpp:356-412): each side sees a boundary face
+                if len(sides) == 1 or pb.bdr_cond.get(tag, 0):
                     vmapP[e, f] = vmapM[e, f]
                     bc[e, f] = pb.bdr_cond.get(tag, 0)
                     continue

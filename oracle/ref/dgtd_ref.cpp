@@ -177,6 +177,8 @@ struct Factory
    FiniteElementSpace &fes;
    int dim, N;
    std::map<BC, Array<int>> bdrMarker;   // Model::getBoundaryToMarker (true boundary faces only)
+   std::map<BC, Array<int>> ibMarker;    // Model::getInteriorBoundaryToMarker (PEC/PMC/SMA sheets inside the mesh)
+   Array<int> ignoreMarker;              // buildInteriorIgnoreMarker (:373-389): faces the regular interior flux skips
    Array<int> tfsfMarker;
 
    Factory(Problem &p, FiniteElementSpace &f) : pd(p), fes(f)
@@ -184,22 +186,24 @@ struct Factory
       Mesh &m = *fes.GetMesh();
       dim = m.Dimension(); N = fes.GetNDofs();
       int nattr = m.bdr_attributes.Size() ? m.bdr_attributes.Max() : 0;
-      for (auto &kv : pd.bdr)
-      {
-         if (kv.first > nattr) { continue; }
-         auto &mk = bdrMarker[kv.second];
-         if (mk.Size() == 0) { mk.SetSize(nattr); mk = 0; }
-         mk[kv.first - 1] = 1;
-      }
-      // sanity: listed boundary attributes must sit on true boundary faces
+      // driver.cpp:1012-1041: a boundary tag is INTERIOR when one of its boundary elements lies on an interior face
+      std::set<int> interiorTag;
       for (int be = 0; be < m.GetNBE(); be++)
       {
          int a = m.GetBdrAttribute(be);
-         if (pd.bdr.count(a))
-         {
-            int f = m.GetBdrElementFaceIndex(be), e1, e2; m.GetFaceElements(f, &e1, &e2);
-            if (e2 >= 0) { MFEM_ABORT("oracle: interior PEC/PMC/SMA boundaries are not restated (attr " << a << ")"); }
-         }
+         if (pd.bdr.count(a) && m.FaceIsInterior(m.GetBdrElementFaceIndex(be))) { interiorTag.insert(a); }
+      }
+      for (auto &kv : pd.bdr)
+      {
+         if (kv.first > nattr) { continue; }
+         auto &mk = interiorTag.count(kv.first) ? ibMarker[kv.second] : bdrMarker[kv.second];
+         if (mk.Size() == 0) { mk.SetSize(nattr); mk = 0; }
+         mk[kv.first - 1] = 1;
+      }
+      if (!ibMarker.empty())
+      {
+         ignoreMarker.SetSize(nattr); ignoreMarker = 0;
+         for (auto &kv : ibMarker) for (int i = 0; i < nattr; i++) { if (kv.second[i] == 1) { ignoreMarker[i] = 1; } }
       }
       if (!pd.tfsf_tags.empty())
       {
@@ -236,7 +240,8 @@ struct Factory
    std::unique_ptr<BilinearForm> ZeroNormal(int f)
    {
       auto r = std::make_unique<BilinearForm>(&fes);
-      r->AddInteriorFaceIntegrator(new mx::MaxwellDGZeroNormalJumpIntegrator(pd.alpha));
+      if (ignoreMarker.Size() > 0) { r->AddInteriorFaceIntegrator(new mx::MaxwellDGZeroNormalJumpIntegrator(pd.alpha), ignoreMarker); }
+      else { r->AddInteriorFaceIntegrator(new mx::MaxwellDGZeroNormalJumpIntegrator(pd.alpha)); }
       for (auto &kv : bdrMarker)
       {
          double c = kv.first != BC_SMA ? bdrCoeff(kv.first, f) * pd.alpha : 1.0;
@@ -250,7 +255,8 @@ struct Factory
    {
       std::vector<Direction> dt{Direction(x)};
       auto r = std::make_unique<BilinearForm>(&fes);
-      r->AddInteriorFaceIntegrator(new mx::MaxwellDGOneNormalJumpIntegrator(dt, 1.0));
+      if (ignoreMarker.Size() > 0) { r->AddInteriorFaceIntegrator(new mx::MaxwellDGOneNormalJumpIntegrator(dt, 1.0), ignoreMarker); }
+      else { r->AddInteriorFaceIntegrator(new mx::MaxwellDGOneNormalJumpIntegrator(dt, 1.0)); }
       for (auto &kv : bdrMarker)
       {
          double c = kv.first != BC_SMA ? bdrCoeff(kv.first, f) : 1.0;
@@ -264,7 +270,8 @@ struct Factory
    {
       std::vector<Direction> dt{Direction(d), Direction(d2)};
       auto r = std::make_unique<BilinearForm>(&fes);
-      r->AddInteriorFaceIntegrator(new mx::MaxwellDGTwoNormalJumpIntegrator(dt, pd.alpha));
+      if (ignoreMarker.Size() > 0) { r->AddInteriorFaceIntegrator(new mx::MaxwellDGTwoNormalJumpIntegrator(dt, pd.alpha), ignoreMarker); }
+      else { r->AddInteriorFaceIntegrator(new mx::MaxwellDGTwoNormalJumpIntegrator(dt, pd.alpha)); }
       for (auto &kv : bdrMarker)
       {
          double c = kv.first != BC_SMA ? bdrCoeff(kv.first, f) * pd.alpha : 1.0;
@@ -272,6 +279,40 @@ struct Factory
       }
       r->Assemble(); r->Finalize();
       return r;
+   }
+   // interior-boundary forms (:575-675): MaxwellDGInteriorJumpIntegrator keeps the two self blocks only, i.e. each side
+   // of the sheet sees a boundary face with the true-boundary coefficients (SMA: 1.0 regardless of alpha)
+   std::unique_ptr<BilinearForm> IBZero(int f)
+   {
+      auto r = std::make_unique<BilinearForm>(&fes);
+      for (auto &kv : ibMarker)
+      {
+         double c = kv.first != BC_SMA ? bdrCoeff(kv.first, f) * pd.alpha : 1.0;
+         r->AddInternalBoundaryFaceIntegrator(new mx::MaxwellDGInteriorJumpIntegrator({}, c), kv.second);
+      }
+      r->Assemble(); r->Finalize(); return r;
+   }
+   std::unique_ptr<BilinearForm> IBOne(int f, int x)
+   {
+      std::vector<Direction> dt{Direction(x)};
+      auto r = std::make_unique<BilinearForm>(&fes);
+      for (auto &kv : ibMarker)
+      {
+         double c = kv.first != BC_SMA ? bdrCoeff(kv.first, f) : 1.0;
+         r->AddInternalBoundaryFaceIntegrator(new mx::MaxwellDGInteriorJumpIntegrator(dt, c), kv.second);
+      }
+      r->Assemble(); r->Finalize(); return r;
+   }
+   std::unique_ptr<BilinearForm> IBTwo(int f, int d, int d2)
+   {
+      std::vector<Direction> dt{Direction(d), Direction(d2)};
+      auto r = std::make_unique<BilinearForm>(&fes);
+      for (auto &kv : ibMarker)
+      {
+         double c = kv.first != BC_SMA ? bdrCoeff(kv.first, f) * pd.alpha : 1.0;
+         r->AddInternalBoundaryFaceIntegrator(new mx::MaxwellDGInteriorJumpIntegrator(dt, c), kv.second);
+      }
+      r->Assemble(); r->Finalize(); return r;
    }
    // sigma mass (:  buildSigmaMassOperator) — PW sigma per attribute
    std::unique_ptr<BilinearForm> SigmaMass()
@@ -360,6 +401,37 @@ static std::unique_ptr<SparseMatrix> buildGlobal(Factory &F)
    std::unique_ptr<BilinearForm> MI[2] = {F.MInv(FE), F.MInv(FH)};
    auto place = [&](SparseMatrix *op, int fr, int dr, int fc, int dc, double s)
    { blocks.push_back({std::make_unique<SparseMatrix>(*op), (3 * fr + dr) * N, (3 * fc + dc) * N, s}); };
+   // interior boundaries first (:1444-1484, collectGlobal{One,Zero,Two}NormalIBFIOperators :1214-1265): same block
+   // placement and signs as the regular flux forms
+   if (!F.ibMarker.empty())
+   {
+      for (int f : {FE, FH}) for (int x = 0; x < 3; x++)
+      {
+         if (x >= dim) { continue; }
+         int y = (x + 1) % 3, z = (x + 2) % 3;
+         auto B = F.IBOne(alt(f), x);
+         std::unique_ptr<SparseMatrix> op(prod(*MI[f], *B));
+         place(op.get(), f, y, alt(f), z, 1.0 - 2.0 * f);
+         place(op.get(), f, z, alt(f), y, -1.0 + 2.0 * f);
+      }
+      for (int f : {FE, FH})
+      {
+         auto B = F.IBZero(f);
+         std::unique_ptr<SparseMatrix> op(prod(*MI[f], *B));
+         for (int d = 0; d < 3; d++) { place(op.get(), f, d, f, d, -1.0); }
+      }
+      for (int f : {FE, FH}) for (int d = 0; d < 3; d++)
+      {
+         if (d >= dim) { continue; }
+         for (int d2 = 0; d2 < 3; d2++)
+         {
+            if (d2 >= dim) { continue; }
+            auto B = F.IBTwo(f, d, d2);
+            std::unique_ptr<SparseMatrix> op(prod(*MI[f], *B));
+            place(op.get(), f, d, f, d2, 1.0);
+         }
+      }
+   }
    // directional (:1268-1289)
    for (int f : {FE, FH}) for (int x = 0; x < 3; x++)
    {

@@ -74,6 +74,91 @@ def tfsf_box_mesh(path, n=4, lo=0.25, hi=0.75):
         for v in verts: f.write("%.17g %.17g %.17g\n" % v)
 
 
+def sheet_mesh(path, n=4):
+    """n^3 Kuhn box with three open sheets of interior faces listed as boundary elements: attribute 7 on the plane x = 1/2
+    (y <= 1/2), 8 on y = 1/2 (z >= 1/2), 9 on z = 1/4 (x >= 1/2) — interior PEC / PMC / SMA boundaries."""
+    vid = lambda i, j, k: (k * (n + 1) + j) * (n + 1) + i
+    verts = [(i / n, j / n, k / n) for k in range(n + 1) for j in range(n + 1) for i in range(n + 1)]
+    perms = [(0, 1, 2), (0, 2, 1), (1, 0, 2), (1, 2, 0), (2, 0, 1), (2, 1, 0)]
+    tets, faces = [], {}
+    for k in range(n):
+        for j in range(n):
+            for i in range(n):
+                for pm in perms:
+                    c = [0, 0, 0]; v = [vid(i, j, k)]
+                    for s in pm:
+                        c[s] = 1; v.append(vid(i + c[0], j + c[1], k + c[2]))
+                    tets.append(v)
+    for t in tets:
+        for f in range(4):
+            faces.setdefault(tuple(sorted(t[:f] + t[f + 1:])), []).append(t)
+    V = np.array(verts)
+    bdr = []
+    for key, ts in faces.items():
+        P = V[list(key)]
+        if len(ts) == 1:
+            for ax in range(3):
+                if np.all(P[:, ax] == 0.0): bdr.append((1 + 2 * ax, key))
+                elif np.all(P[:, ax] == 1.0): bdr.append((2 + 2 * ax, key))
+        elif np.all(P[:, 0] == 0.5) and np.all(P[:, 1] <= 0.5): bdr.append((7, key))
+        elif np.all(P[:, 1] == 0.5) and np.all(P[:, 2] >= 0.5): bdr.append((8, key))
+        elif np.all(P[:, 2] == 0.25) and np.all(P[:, 0] >= 0.5): bdr.append((9, key))
+    with open(path, "w") as f:
+        f.write("MFEM mesh v1.0\n\ndimension\n3\n\nelements\n%d\n" % len(tets))
+        for t in tets: f.write("1 4 %d %d %d %d\n" % tuple(t))
+        f.write("\nboundary\n%d\n" % len(bdr))
+        for a, k in bdr: f.write("%d 2 %d %d %d\n" % ((a,) + k))
+        f.write("\nvertices\n%d\n3\n" % len(verts))
+        for v in verts: f.write("%.17g %.17g %.17g\n" % v)
+
+
+def sheet_mesh_2d(path, nx=4, ny=3):
+    """nx x ny squares split into triangles with the interior edges on x = 1/2 (lower half) tagged 5 and on y = 1/3 tagged 6."""
+    vid = lambda i, j: j * (nx + 1) + i
+    verts = [(i / nx, j / ny) for j in range(ny + 1) for i in range(nx + 1)]
+    tris = []
+    for j in range(ny):
+        for i in range(nx):
+            a, b, c, d = vid(i, j), vid(i + 1, j), vid(i + 1, j + 1), vid(i, j + 1)
+            tris += [(a, b, c), (a, c, d)]
+    edges = {}
+    for t in tris:
+        for f in range(3):
+            edges.setdefault(tuple(sorted(t[:f] + t[f + 1:])), []).append(t)
+    V = np.array(verts)
+    bdr = []
+    for key, ts in edges.items():
+        P = V[list(key)]
+        if len(ts) == 1:
+            if np.all(P[:, 1] == 0.0): bdr.append((1, key))
+            elif np.all(P[:, 0] == 1.0): bdr.append((2, key))
+            elif np.all(P[:, 1] == 1.0): bdr.append((3, key))
+            else: bdr.append((4, key))
+        elif np.all(P[:, 0] == 0.5) and np.all(P[:, 1] <= 2.0 / 3 + 1e-12): bdr.append((5, key))
+        elif np.all(np.abs(P[:, 1] - 1.0 / 3) < 1e-12) and np.all(P[:, 0] >= 0.5): bdr.append((6, key))
+    with open(path, "w") as f:
+        f.write("MFEM mesh v1.0\n\ndimension\n2\n\nelements\n%d\n" % len(tris))
+        for t in tris: f.write("1 2 %d %d %d\n" % t)
+        f.write("\nboundary\n%d\n" % len(bdr))
+        for a, k in bdr: f.write("%d 1 %d %d\n" % ((a,) + k))
+        f.write("\nvertices\n%d\n2\n" % len(verts))
+        for v in verts: f.write("%.17g %.17g\n" % v)
+
+
+def interior_cases():
+    """Interior PEC / PMC / SMA boundaries (DGOperatorFactory.h:575-675): sheets and a closed box inside the mesh."""
+    with tempfile.TemporaryDirectory() as d:
+        mp = os.path.join(d, "sheets.mesh"); sheet_mesh(mp)
+        run("ibc3d_p3_mixed_sheets", f"--mesh {mp} --order 3 --alpha 0.6 --bdr 1:pec,2:sma,3:pmc,4:pec,5:sma,6:pec,7:pec,8:pmc,9:sma --init random:11 --dt 1e-3 --steps 2".split(),
+            {"bdr": {"1": "pec", "2": "sma", "3": "pmc", "4": "pec", "5": "sma", "6": "pec", "7": "pec", "8": "pmc", "9": "sma"}})
+        mb = os.path.join(d, "box.mesh"); tfsf_box_mesh(mb)
+        run("ibc3d_p2_pec_box", f"--mesh {mb} --order 2 --alpha 1.0 --bdr 1:sma,2:sma,3:sma,4:sma,5:sma,6:sma,7:pec --init random:12 --dt 2e-3 --steps 3".split(),
+            {"bdr": {"1": "sma", "2": "sma", "3": "sma", "4": "sma", "5": "sma", "6": "sma", "7": "pec"}})
+        m2 = os.path.join(d, "sheets2d.mesh"); sheet_mesh_2d(m2)
+        run("ibc2d_p3_sheets", f"--mesh {m2} --order 3 --alpha 1.0 --bdr 1:pec,2:sma,3:pmc,4:pec,5:pec,6:sma --init random:13 --dt 1e-3 --steps 2".split(),
+            {"bdr": {"1": "pec", "2": "sma", "3": "pmc", "4": "pec", "5": "pec", "6": "sma"}})
+
+
 def two_material_mesh(path):
     """2x2x2 Kuhn box, elements with barycentre x > 0.5 get attribute 2."""
     n = 2
@@ -112,6 +197,9 @@ def two_material_mesh(path):
 if __name__ == "__main__":
     if not os.path.exists(REF):
         sys.exit("build oracle/_ref first: make -C oracle/ref")
+    if len(sys.argv) > 1 and sys.argv[1] == "interior":
+        interior_cases()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "config2":
         # config 2 of BASELINE.json on the reference's own gmsh triangle mesh: 2D_PEC.json (246 triangles, order 3, upwind,
         # global operator, PEC on tags 2,4 and PMC on 1,3, Gaussian E_z of spread 0.12 varying along x, dt 1e-3)
