@@ -282,6 +282,28 @@ class Evolution:
         _ck(lib.dgtd_get_state_local(self._h, _dp(out)))
         return out
 
+    def set_state_parlocal(self, x):
+        """local vector [6][n_local], owned elements by ascending global id (the rank's mfem::ParMesh order)"""
+        x = np.ascontiguousarray(x, np.float64)
+        if x.size != 6 * self.n_local:
+            raise DgtdError(-1, "set_state_parlocal: wrong size")
+        _ck(lib.dgtd_set_state_parlocal(self._h, _dp(x)))
+
+    def get_state_parlocal(self, out=None):
+        if out is None:
+            out = np.zeros(6 * self.n_local)
+        _ck(lib.dgtd_get_state_parlocal(self._h, _dp(out)))
+        return out
+
+    def Mult_parlocal(self, x, out=None):
+        x = np.ascontiguousarray(x, np.float64)
+        if x.size != 6 * self.n_local:
+            raise DgtdError(-1, "Mult_parlocal: wrong size")
+        if out is None:
+            out = np.zeros(6 * self.n_local)
+        _ck(lib.dgtd_mult_parlocal(self._h, C.c_double(self._t), _dp(x), _dp(out)))
+        return out
+
     def Step(self, t, dt):
         _ck(lib.dgtd_rk4_step(self._h, C.c_double(t), C.c_double(dt)))
         return t + dt

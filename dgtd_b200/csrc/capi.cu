@@ -11,6 +11,7 @@
 #include "kernels_wh.cuh"
 
 #include <dlfcn.h>
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -117,10 +118,20 @@ static KernelSet select_kernels(int dim, int p)
 // the warp-per-group kernel: tetrahedra of order 1..4, element-major "aos" layout, one warp per group of 8 elements
 typedef void (*WgFn)(const WgArgs);
 struct WgSet { WgFn fn[4]; int threads; size_t smem; };
-template <int P, bool TF> static WgSet wgset()
+template <int P, bool TF, bool DX = false> static WgSet wgset()
 {
-    using B = Wg<P>;
-    return {{stage_wg_kernel<P, 0, TF>, stage_wg_kernel<P, 1, TF>, stage_wg_kernel<P, 2, TF>, stage_wg_kernel<P, 3, TF>}, B::T, B::smem_bytes};
+    using B = Wg<P, DX>;
+    return {{stage_wg_kernel<P, 0, TF, DX>, stage_wg_kernel<P, 1, TF, DX>, stage_wg_kernel<P, 2, TF, DX>, stage_wg_kernel<P, 3, TF, DX>}, B::T, B::smem_bytes};
+}
+// the same kernel with x / z through direct global accesses (kernels_wg.cuh: DX): 12 instead of 8 warps per SM at order <= 3
+static bool select_wgx(int dim, int p, bool tf, WgSet &ws)
+{
+    if (dim != 3) return false;
+    switch (p) {
+        case 1: ws = tf ? wgset<1, true, true>() : wgset<1, false, true>(); return true; case 2: ws = tf ? wgset<2, true, true>() : wgset<2, false, true>(); return true;
+        case 3: ws = tf ? wgset<3, true, true>() : wgset<3, false, true>(); return true; case 4: ws = tf ? wgset<4, true, true>() : wgset<4, false, true>(); return true;
+    }
+    return false;
 }
 // tf = the context injects a TF/SF plane wave
 static bool select_wg(int dim, int p, bool tf, WgSet &ws)
@@ -155,6 +166,7 @@ struct dgtd_ctx {
     HostOp H;
     WgPlan WP;
     bool has_sigma = false;
+    bool wgx = false;                // ... with x / z through direct global accesses (12 warps per SM)
     bool wh = false;                 // ... or its half-row form (kernels_wh.cuh, groups of 4 elements); wg stays set: same plan and layout
     int wg_groups_per_cta = 0;
     bool wg = false;                 // aos layout + warp-per-group kernel (the state needs a layout conversion at the ABI)
@@ -190,7 +202,7 @@ struct dgtd_ctx {
     DevBuf<unsigned int> p2p_done, p2p_cnt;         // last-CTA election of the stand-alone push kernel; per-peer arrival counters of the fused push
     DevBuf<int> worder;                              // WgPlan::order (multi-rank contexts: partition-face groups first)
     DevBuf<int> p2p_err;
-    DevBuf<int> hpush, dgid;                         // dgid: local element -> caller's element index (H.elem_gid)
+    DevBuf<int> hpush, dgid, dlidx;                  // dgid: local element -> caller's element index (H.elem_gid); dlidx: -> its rank among the owned elements by global id
     long long launches = 0;
     std::vector<double> hostbuf;     // staging of the by-element gather/scatter of multi-rank contexts
     DevBuf<int> flagbuf;             // one int: collective verdicts (run_until's stability flag, teardown barriers)
@@ -413,32 +425,34 @@ static void from_device_layout(dgtd_ctx *c, const double *dev, double *ref, cons
     c->launches++;
 }
 
-// host vector [6][Nloc] <-> device state (reference layout, or aos through a staging buffer).  caller_order: the
-// host vector is in the caller's (global) element order of a single-rank context
-static void upload_local(dgtd_ctx *c, const double *hloc, double *dev, bool caller_order = false)
+// host vector [6][Nloc] <-> device state (reference layout, or aos through a staging buffer).  perm = nullptr: the host
+// vector is in this rank's own (Morton) element order; otherwise local element le is element perm[le] of the host vector
+// (dgid: caller's global order of a single-rank context; dlidx: the owned elements by ascending global id = the element
+// order of the rank's mfem::ParMesh)
+static void upload_local(dgtd_ctx *c, const double *hloc, double *dev, const int *perm = nullptr)
 {
     const long long Nl = c->Nloc;
     if (c->pushed == dev) c->pushed = nullptr;
-    if (!c->wg && !caller_order) {
+    if (!c->wg && !perm) {
         CU(cudaMemcpyAsync(dev, hloc, sizeof(double) * 6 * Nl, cudaMemcpyHostToDevice, c->stream));
     } else {
         if (c->stage_ref.n != (size_t)6 * Nl) c->stage_ref.alloc((size_t)6 * Nl);
         CU(cudaMemcpyAsync(c->stage_ref.p, hloc, sizeof(double) * 6 * Nl, cudaMemcpyHostToDevice, c->stream));
-        if (c->wg) to_device_layout(c, c->stage_ref.p, dev, caller_order ? c->dgid.p : nullptr);
-        else { permute_elements_kernel<<<1184, 256, 0, c->stream>>>(c->stage_ref.p, c->dgid.p, c->H.Np, c->H.NEloc, Nl, 1, dev); c->launches++; }
+        if (c->wg) to_device_layout(c, c->stage_ref.p, dev, perm);
+        else { permute_elements_kernel<<<1184, 256, 0, c->stream>>>(c->stage_ref.p, perm, c->H.Np, c->H.NEloc, Nl, 1, dev); c->launches++; }
     }
     CU(cudaStreamSynchronize(c->stream));
 }
-static void download_local(dgtd_ctx *c, const double *dev, double *hloc, bool caller_order = false)
+static void download_local(dgtd_ctx *c, const double *dev, double *hloc, const int *perm = nullptr)
 {
     const long long Nl = c->Nloc;
     p2p_check(c);
-    if (!c->wg && !caller_order) {
+    if (!c->wg && !perm) {
         CU(cudaMemcpyAsync(hloc, dev, sizeof(double) * 6 * Nl, cudaMemcpyDeviceToHost, c->stream));
     } else {
         if (c->stage_ref.n != (size_t)6 * Nl) c->stage_ref.alloc((size_t)6 * Nl);
-        if (c->wg) from_device_layout(c, dev, c->stage_ref.p, caller_order ? c->dgid.p : nullptr);
-        else { permute_elements_kernel<<<1184, 256, 0, c->stream>>>(dev, c->dgid.p, c->H.Np, c->H.NEloc, Nl, 0, c->stage_ref.p); c->launches++; }
+        if (c->wg) from_device_layout(c, dev, c->stage_ref.p, perm);
+        else { permute_elements_kernel<<<1184, 256, 0, c->stream>>>(dev, perm, c->H.Np, c->H.NEloc, Nl, 0, c->stage_ref.p); c->launches++; }
         CU(cudaMemcpyAsync(hloc, c->stage_ref.p, sizeof(double) * 6 * Nl, cudaMemcpyDeviceToHost, c->stream));
     }
     CU(cudaStreamSynchronize(c->stream));
@@ -448,7 +462,7 @@ static void scatter_to_device(dgtd_ctx *c, const double *host, double *dev)
 {
     const int Np = c->H.Np; const long long Ng = c->Nglob, Nl = c->Nloc;
     if (c->identity) { upload_local(c, host, dev); return; }
-    if (c->nranks == 1) { upload_local(c, host, dev, true); return; }   // the permutation runs on the device
+    if (c->nranks == 1) { upload_local(c, host, dev, c->dgid.p); return; }   // the permutation runs on the device
     c->hostbuf.resize((size_t)6 * Nl);
     for (int comp = 0; comp < 6; comp++)
         for (int le = 0; le < c->H.NEloc; le++)
@@ -459,7 +473,7 @@ static void gather_from_device(dgtd_ctx *c, const double *dev, double *host)
 {
     const int Np = c->H.Np; const long long Ng = c->Nglob, Nl = c->Nloc;
     if (c->identity) { download_local(c, dev, host); return; }
-    if (c->nranks == 1) { download_local(c, dev, host, true); return; }
+    if (c->nranks == 1) { download_local(c, dev, host, c->dgid.p); return; }
     c->hostbuf.resize((size_t)6 * Nl);
     download_local(c, dev, c->hostbuf.data());
     for (int comp = 0; comp < 6; comp++)
@@ -600,6 +614,11 @@ int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
         c->WP = build_wg_plan(H);
         if (c->WP.ntab <= Wg<3>::TABROWS) c->wg = c->wh = true;
     }
+    if (!c->wg && ksel == "wgx" && select_wgx(H.dim, H.p, has_tf, c->wgs) && c->wgs.smem <= (size_t)prop.sharedMemPerBlockOptin) {
+        c->WP = build_wg_plan(H);
+        c->wg_groups_per_cta = c->wgs.threads / 32;
+        if (c->WP.ntab <= Wg<3>::TABROWS) c->wg = c->wgx = true;
+    }
     if (!c->wg && (ksel == "wg" || ksel == "wh" || ksel.empty()) && select_wg(H.dim, H.p, has_tf, c->wgs) && c->wgs.smem <= (size_t)prop.sharedMemPerBlockOptin) {
         c->WP = build_wg_plan(H);
         c->wg_groups_per_cta = c->wgs.threads / 32;
@@ -641,6 +660,12 @@ int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
     CU(cudaMemset(c->gate.p, 0, 4 * sizeof(double)));
     c->send_node.upload(H.send_node, 1);
     c->dgid.upload(H.elem_gid, 1);
+    {   // the rank's mfem::ParMesh numbers its elements by ascending global id (ParMesh(comm, mesh, partitioning))
+        std::vector<int> sorted(H.elem_gid), lidx((size_t)H.NEloc);
+        std::sort(sorted.begin(), sorted.end());
+        for (int le = 0; le < H.NEloc; le++) lidx[(size_t)le] = (int)(std::lower_bound(sorted.begin(), sorted.end(), H.elem_gid[(size_t)le]) - sorted.begin());
+        c->dlidx.upload(lidx, 1);
+    }
     const size_t hn = std::max<size_t>(1, (size_t)6 * H.n_halo_faces * H.Nfp);
     c->halo.alloc(hn); c->sendbuf.alloc(hn); c->scratch.alloc(4); c->flagbuf.alloc(1);
     CU(cudaMemset(c->halo.p, 0, hn * sizeof(double)));
@@ -723,6 +748,35 @@ int dgtd_get_state_local(dgtd_ctx *c, double *h)
     if (!c || !h) throw Error(DGTD_ERR_ARG, "null argument");
     CU(cudaSetDevice(c->device));
     download_local(c, c->x.p, h);
+    GUARD_END
+}
+int dgtd_set_state_parlocal(dgtd_ctx *c, const double *h)
+{
+    GUARD_BEGIN
+    if (!c || !h) throw Error(DGTD_ERR_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    upload_local(c, h, c->x.p, c->dlidx.p);
+    GUARD_END
+}
+int dgtd_get_state_parlocal(dgtd_ctx *c, double *h)
+{
+    GUARD_BEGIN
+    if (!c || !h) throw Error(DGTD_ERR_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    download_local(c, c->x.p, h, c->dlidx.p);
+    GUARD_END
+}
+int dgtd_mult_parlocal(dgtd_ctx *c, double t, const double *in, double *out)
+{
+    GUARD_BEGIN
+    if (!c || !in || !out) throw Error(DGTD_ERR_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    const size_t n6 = (size_t)6 * c->Nalloc;
+    c->pushed = nullptr;
+    if (c->tmp_in.n != n6) { c->tmp_in.alloc(n6); c->tmp_out.alloc(n6); }
+    upload_local(c, in, c->tmp_in.p, c->dlidx.p);
+    mult_device(c, t, c->tmp_in.p, c->tmp_out.p);
+    download_local(c, c->tmp_out.p, out, c->dlidx.p);
     GUARD_END
 }
 int dgtd_state_device_ptr(dgtd_ctx *c, double **dev)
@@ -976,8 +1030,9 @@ int dgtd_kernel_info(const dgtd_ctx *c, char *buf, int cap)
         std::snprintf(tmp, sizeof tmp, "stage_wh_kernel<P=%d,MODE> DMMA m8n8k4 transposed, warp per group of 4 elements (rows = element x field), aos layout, %d threads, %zu B smem, grid %d%s",
                       c->H.p, c->wgs.threads, c->wgs.smem, c->grid, c->nranks == 1 ? "" : c->p2p ? ", halo: fused peer-memory stores" : ", halo: NCCL send/recv");
     else if (c->wg)
-        std::snprintf(tmp, sizeof tmp, "stage_wg_kernel<P=%d,MODE> DMMA m8n8k4 transposed, warp per group of 8 elements, aos layout, %d threads, %zu B smem, grid %d%s",
-                      c->H.p, c->wgs.threads, c->wgs.smem, c->grid, c->nranks == 1 ? "" : c->p2p ? ", halo: fused peer-memory stores" : ", halo: NCCL send/recv");
+        std::snprintf(tmp, sizeof tmp, "stage_wg_kernel<P=%d,MODE%s> DMMA m8n8k4 transposed, warp per group of 8 elements, aos layout%s, %d threads, %zu B smem, grid %d%s",
+                      c->H.p, c->wgx ? ",DX" : "", c->wgx ? ", x/z by direct global accesses" : "", c->wgs.threads, c->wgs.smem, c->grid,
+                      c->nranks == 1 ? "" : c->p2p ? ", halo: fused peer-memory stores" : ", halo: NCCL send/recv");
     else
         std::snprintf(tmp, sizeof tmp, "stage_kernel<DIM=%d,P=%d,MODE> generic, %d threads, %zu B smem, grid %d", c->H.dim, c->H.p, c->ks.threads, c->ks.smem, c->grid);
     std::snprintf(buf, (size_t)cap, "%s", tmp);

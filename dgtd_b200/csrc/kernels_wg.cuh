@@ -142,17 +142,25 @@ struct WgArgs {
     WgP2P pp;
 };
 
-template <int P> struct Wg {
+// DX ("direct x/z"): only y_in is staged in shared memory; x and z are read and y_out / z written with per-lane 128-bit
+// global accesses in the epilogue (the four lanes of an element cover 192 contiguous bytes = 6 whole sectors per node slot).
+// A warp then needs 10 KB instead of 25 KB of shared memory, so 12 warps (3 per scheduler) fit at order <= 3 and 8 at order 4
+// instead of 8 / 4: the FP64 pipe idles whenever every warp of a scheduler sits in a load wait or in the epilogue.
+template <int P, bool DX = false> struct Wg {
     static constexpr int Np = (P + 1) * (P + 2) * (P + 3) / 6, Nfp = (P + 1) * (P + 2) / 2;
     static constexpr int NT = (Np + 7) / 8, KSV = (Np + 3) / 4, VT = (NT - 1) * 3 + 3;
 #ifndef DGTD_WG_NW
 #define DGTD_WG_NW 8
 #endif
-    static constexpr int NW = P <= 3 ? DGTD_WG_NW : 4, T = 32 * NW;       // warps per CTA = groups in flight per SM
+#ifndef DGTD_WGX_NW
+#define DGTD_WGX_NW 12
+#endif
+    static constexpr int NW = DX ? (P <= 3 ? DGTD_WGX_NW : 8) : (P <= 3 ? DGTD_WG_NW : 4), T = 32 * NW;   // warps per CTA = groups in flight per SM
     static constexpr int GS = Np * BLK_E * 6;                    // doubles per group of one state vector
     static constexpr int NFV = KSV * VT, NFL = Nfp * NT, NFR = NFV + NFL;
     static constexpr int WGEO = BLK_E * WG_GEO, WDESC = BLK_E * 4 * 2;   // doubles / ints per group
-    static constexpr int WDBL = 3 * GS + WGEO + WDESC / 2;       // doubles per warp: Y, X, Z, geometry, descriptors
+    static constexpr int NBUF = DX ? 1 : 3;                      // group buffers per warp: Y [, X, Z]
+    static constexpr int WDBL = NBUF * GS + WGEO + WDESC / 2;    // doubles per warp: buffers, geometry, descriptors
     static constexpr int TABROWS = 136;
     static constexpr int oWarp = NFR * 32;
     static constexpr size_t bTab = (size_t)(oWarp + NW * WDBL) * 8;
@@ -187,6 +195,22 @@ __device__ __forceinline__ void load_rec_split(const double *p, bool in_smem, do
                      : "=d"(u[0]), "=d"(u[1]), "=d"(u[2]), "=d"(u[3]), "=d"(u[4]), "=d"(u[5]) : "l"(p));
     }
 }
+__device__ __forceinline__ void load_rec_global(const double *p, double *u)
+{
+    asm volatile("ld.global.v2.f64 {%0,%1}, [%6];\n\tld.global.v2.f64 {%2,%3}, [%6+16];\n\tld.global.v2.f64 {%4,%5}, [%6+32];"
+                 : "=d"(u[0]), "=d"(u[1]), "=d"(u[2]), "=d"(u[3]), "=d"(u[4]), "=d"(u[5]) : "l"(p));
+}
+// records another lane of this warp has just written (after __syncwarp): L2, not a possibly stale L1 line
+__device__ __forceinline__ void load_rec_global_cg(const double *p, double *u)
+{
+    asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%6];\n\tld.global.cg.v2.f64 {%2,%3}, [%6+16];\n\tld.global.cg.v2.f64 {%4,%5}, [%6+32];"
+                 : "=d"(u[0]), "=d"(u[1]), "=d"(u[2]), "=d"(u[3]), "=d"(u[4]), "=d"(u[5]) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void store_rec_global(double *p, const double *u)
+{
+    asm volatile("st.global.v2.f64 [%0], {%1,%2};\n\tst.global.v2.f64 [%0+16], {%3,%4};\n\tst.global.v2.f64 [%0+32], {%5,%6};"
+                 ::"l"(p), "d"(u[0]), "d"(u[1]), "d"(u[2]), "d"(u[3]), "d"(u[4]), "d"(u[5]) : "memory");
+}
 __device__ __forceinline__ void store_rec(double *p, const double *u)
 {
     double2 *q = reinterpret_cast<double2 *>(p);
@@ -199,18 +223,22 @@ __device__ __forceinline__ void store_rec(double *p, const double *u)
 // Measured alternatives (profiles/): one-step prefetch issued inside the face loop with the flux in physical
 // components, 97.9 G vs 110 G; asm-volatile (pinned) prefetch loads, +-0; prefetch.global.L1 of the records, -9 %.
 // TF: the context has a TF/SF plane-wave source (the injection code sits in the face loop only then).
-template <int P, int MODE, bool TF>
-__global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
+template <int P, int MODE, bool TF, bool DX>
+__global__ void __launch_bounds__(Wg<P, DX>::T, 1) stage_wg_kernel(const WgArgs A)
 {
-    using B = Wg<P>;
+    using B = Wg<P, DX>;
     constexpr int Np = B::Np, Nfp = B::Nfp, NT = B::NT, KSV = B::KSV, VT = B::VT, GS = B::GS;
     constexpr int NL = Np - 8 * (NT - 1);                                          // nodes of the mixed tile
 #ifndef DGTD_WG_PF
 #define DGTD_WG_PF 3
 #endif
-    constexpr int PF = P >= 4 ? 1 : DGTD_WG_PF;                                    // neighbour-record prefetch distance (face steps)
-    constexpr bool LOAD_X = MODE == MODE_STAGE1 || MODE == MODE_STAGE23;           // stage 1: x == y_in, fetched again (L2 hit)
-    constexpr bool LOAD_Z = MODE == MODE_STAGE23 || MODE == MODE_STAGE4;
+#ifndef DGTD_WGX_PF
+#define DGTD_WGX_PF 3
+#endif
+    constexpr int PF = P >= 4 ? 1 : DX ? DGTD_WGX_PF : DGTD_WG_PF;                 // neighbour-record prefetch distance (face steps)
+    constexpr bool NEED_X = MODE == MODE_STAGE1 || MODE == MODE_STAGE23;           // stage 1: x == y_in, fetched again (L2 hit)
+    constexpr bool NEED_Z = MODE == MODE_STAGE23 || MODE == MODE_STAGE4;
+    constexpr bool LOAD_X = NEED_X && !DX, LOAD_Z = NEED_Z && !DX;                 // staged through shared memory by bulk-TMA
     constexpr bool STORE_X = MODE != MODE_STAGE4, STORE_Z = MODE != MODE_MULT;      // stage 4 forms the new x in the z buffer
     extern __shared__ __align__(128) unsigned char smem_wg[];
     double *sm = reinterpret_cast<double *>(smem_wg);
@@ -218,7 +246,7 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
     const uint4 *sTab = reinterpret_cast<const uint4 *>(smem_wg + B::bTab);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, e = lane >> 2, j = lane & 3;
-    double *wY = sm + B::oWarp + warp * B::WDBL, *wX = wY + GS, *wZ = wX + GS, *wGeo = wZ + GS;
+    double *wY = sm + B::oWarp + warp * B::WDBL, *wX = wY + GS, *wZ = wX + GS, *wGeo = wY + B::NBUF * GS;   // DX: no wX / wZ
     const int2 *wDesc = reinterpret_cast<const int2 *>(wGeo + B::WGEO);
     uint64_t *barY = reinterpret_cast<uint64_t *>(smem_wg + B::bBar) + 2 * warp, *barXZ = barY + 1;
 
@@ -434,83 +462,111 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
             if (lane == 0 && gnext >= 0) issue_y(gnext);
         }
         if (LOAD_X || LOAD_Z) mbar_wait(barXZ, par);
+        // node slots of lane (e, j): nodes 8 nt + j and 8 nt + j + 4 of the full tiles, then node 8 (NT-1) + j of the mixed one
+        constexpr int NS = 2 * (NT - 1) + 1;
+        const double *gX = DX ? (MODE == MODE_STAGE1 ? A.yin : A.x) + (size_t)g * GS + e * Np * 6 : nullptr;    // my element's records
+        const double *gZ = DX && NEED_Z ? A.z + (size_t)g * GS + e * Np * 6 : nullptr;
+        double *gO = DX ? A.yout + (size_t)g * GS + e * Np * 6 : nullptr, *gZo = DX ? A.z + (size_t)g * GS + e * Np * 6 : nullptr;
+        double xq[2][6], zq[2][6];                           // DX: x / z records of the next slot are in flight while this one is updated
+        auto slot_node = [&](int sl) { return sl < NS - 1 ? 8 * (sl >> 1) + j + 4 * (sl & 1) : 8 * (NT - 1) + j; };
+        auto slot_valid = [&](int sl) { return sl < NS - 1 || NL == 4 || j < NL; };
+        if (DX && (NEED_X || NEED_Z)) {
+            if (NEED_X) load_rec_global(gX + slot_node(0) * 6, xq[0]);
+            if (NEED_Z) load_rec_global(gZ + slot_node(0) * 6, zq[0]);
+        }
 #pragma unroll
-        for (int nt = 0; nt < NT; nt++)
+        for (int sl = 0; sl < NS; sl++) {
+            const int nt = sl < NS - 1 ? sl >> 1 : NT - 1, h = sl < NS - 1 ? sl & 1 : 0;
+            const int node = slot_node(sl);
+            if (DX && (NEED_X || NEED_Z) && sl + 1 < NS && slot_valid(sl + 1)) {
+                if (NEED_X) load_rec_global(gX + slot_node(sl + 1) * 6, xq[(sl + 1) & 1]);
+                if (NEED_Z) load_rec_global(gZ + slot_node(sl + 1) * 6, zq[(sl + 1) & 1]);
+            }
+            if (!slot_valid(sl)) continue;
+            double kr[6];
+            if (nt < NT - 1) {
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int node = nt < NT - 1 ? 8 * nt + j + 4 * h : 8 * (NT - 1) + j;
-                if (nt == NT - 1 && h == 1) continue;
-                if (nt == NT - 1 && NL < 4 && j >= NL) continue;
-                double kr[6];
-                if (nt < NT - 1) {
-#pragma unroll
-                    for (int c = 0; c < 6; c++) kr[c] = acc[c][nt][h];
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 6; c++) {
-                        const int f3 = 3 * (c / 3), cc = c % 3;
-                        kr[c] = acc[f3 + (cc + 2) % 3][NT - 1][0] + acc[f3 + (cc + 1) % 3][NT - 1][1];
-                    }
-                }
-                double k[6];     // (J/det) k~ : the material factor det/eps, det/mu joins the Runge-Kutta coefficient below
-#pragma unroll
-                for (int d = 0; d < 3; d++) {
-                    k[d] = fma(jm[3 * d], kr[0], fma(jm[3 * d + 1], kr[1], jm[3 * d + 2] * kr[2]));
-                    k[3 + d] = fma(jm[3 * d], kr[3], fma(jm[3 * d + 1], kr[4], jm[3 * d + 2] * kr[5]));
-                }
-                const int off = (e * Np + node) * 6;
-                double ca[6] = {ae, ae, ae, am, am, am}, cb[6] = {be, be, be, bm, bm, bm};
-                if (keep_y || MODE == MODE_MULT) {       // the plain k is needed: conductivity term, or Mult's output
-                    double uo[6] = {0, 0, 0, 0, 0, 0};
-                    if (keep_y) load_rec(wY + off, uo);
-#pragma unroll
-                    for (int d = 0; d < 3; d++) { k[d] = fma(de, k[d], -(se * uo[d])); k[3 + d] *= dm; }
-#pragma unroll
-                    for (int c = 0; c < 6; c++) { ca[c] = A.a; cb[c] = A.b; }
-                }
-                double xv[6], zv[6], o[6], zn[6];
-                if (LOAD_X) load_rec(wX + off, xv);
-                if (LOAD_Z) load_rec(wZ + off, zv);
+                for (int c = 0; c < 6; c++) kr[c] = acc[c][nt][h];
+            } else {
 #pragma unroll
                 for (int c = 0; c < 6; c++) {
-                    if (MODE == MODE_MULT) o[c] = k[c];
-                    else if (MODE == MODE_STAGE1) { o[c] = fma(ca[c], k[c], xv[c]); zn[c] = fma(cb[c], k[c], xv[c]); }
-                    else if (MODE == MODE_STAGE23) { o[c] = fma(ca[c], k[c], xv[c]); zn[c] = fma(cb[c], k[c], zv[c]); }
-                    else zn[c] = fma(cb[c], k[c], zv[c]);          // stage 4: new x, formed in the z buffer
+                    const int f3 = 3 * (c / 3), cc = c % 3;
+                    kr[c] = acc[f3 + (cc + 2) % 3][NT - 1][0] + acc[f3 + (cc + 1) % 3][NT - 1][1];
                 }
+            }
+            double k[6];     // (J/det) k~ : the material factor det/eps, det/mu joins the Runge-Kutta coefficient below
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                k[d] = fma(jm[3 * d], kr[0], fma(jm[3 * d + 1], kr[1], jm[3 * d + 2] * kr[2]));
+                k[3 + d] = fma(jm[3 * d], kr[3], fma(jm[3 * d + 1], kr[4], jm[3 * d + 2] * kr[5]));
+            }
+            const int off = (e * Np + node) * 6;
+            double ca[6] = {ae, ae, ae, am, am, am}, cb[6] = {be, be, be, bm, bm, bm};
+            if (keep_y || MODE == MODE_MULT) {       // the plain k is needed: conductivity term, or Mult's output
+                double uo[6] = {0, 0, 0, 0, 0, 0};
+                if (keep_y) load_rec(wY + off, uo);
+#pragma unroll
+                for (int d = 0; d < 3; d++) { k[d] = fma(de, k[d], -(se * uo[d])); k[3 + d] *= dm; }
+#pragma unroll
+                for (int c = 0; c < 6; c++) { ca[c] = A.a; cb[c] = A.b; }
+            }
+            double xv[6], zv[6], o[6], zn[6];
+            if (DX) {
+#pragma unroll
+                for (int c = 0; c < 6; c++) { xv[c] = xq[sl & 1][c]; zv[c] = zq[sl & 1][c]; }
+            } else {
+                if (LOAD_X) load_rec(wX + off, xv);
+                if (LOAD_Z) load_rec(wZ + off, zv);
+            }
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                if (MODE == MODE_MULT) o[c] = k[c];
+                else if (MODE == MODE_STAGE1) { o[c] = fma(ca[c], k[c], xv[c]); zn[c] = fma(cb[c], k[c], xv[c]); }
+                else if (MODE == MODE_STAGE23) { o[c] = fma(ca[c], k[c], xv[c]); zn[c] = fma(cb[c], k[c], zv[c]); }
+                else zn[c] = fma(cb[c], k[c], zv[c]);          // stage 4: new x, formed in the z buffer
+            }
+            if (DX) {
+                if (STORE_X) store_rec_global(gO + node * 6, o);
+                if (MODE == MODE_STAGE4) store_rec_global(gO + node * 6, zn);
+                else if (STORE_Z) store_rec_global(gZo + node * 6, zn);
+            } else {
                 if (STORE_X) store_rec(wX + off, o);
                 if (STORE_Z) store_rec(wZ + off, zn);
             }
-        fence_async_smem();
+        }
+        if (!DX) fence_async_smem();
         __syncwarp();
         if (MODE != MODE_MULT && A.pp.signal_epoch != 0 && __any_sync(0xffffffffu, info.x < -1)) {
             if (info.x < -1) {                               // my traces of the new stage vector -> the peer's halo
                 const int2 hp = A.pp.hpush[-2 - info.x];
                 const uint4 prow = sTab[hp.x >> 8];
                 double *dst = A.pp.peer_out[hp.x & 0xff] + (size_t)hp.y * Nfp * 6;
-                const double *src = (MODE == MODE_STAGE4 ? wZ : wX) + e * Np * 6;
+                const double *src = DX ? gO : (MODE == MODE_STAGE4 ? wZ : wX) + e * Np * 6;   // DX: what this warp just stored (L2)
 #pragma unroll
                 for (int m = 0; m < Nfp; m++) {
                     double r[6];
-                    load_rec(src + tab_byte(prow, m) * 6, r);
+                    if (DX) load_rec_global_cg(src + tab_byte(prow, m) * 6, r);
+                    else load_rec(src + tab_byte(prow, m) * 6, r);
                     store_rec(dst + m * 6, r);
                 }
             }
             p2p_arrive(A.pp, mypeer, lane);
         }
         if (lane == 0) {
-            const size_t goff = (size_t)g * GS;
-            if (STORE_X) bulk_store(A.yout + goff, wX, GS * 8);
-            if (MODE == MODE_STAGE4) bulk_store(A.yout + goff, wZ, GS * 8);
-            else if (STORE_Z) bulk_store(A.z + goff, wZ, GS * 8);
-            bulk_commit();
+            if (!DX) {
+                const size_t goff = (size_t)g * GS;
+                if (STORE_X) bulk_store(A.yout + goff, wX, GS * 8);
+                if (MODE == MODE_STAGE4) bulk_store(A.yout + goff, wZ, GS * 8);
+                else if (STORE_Z) bulk_store(A.z + goff, wZ, GS * 8);
+                bulk_commit();
+            }
             if (keep_y && gnext >= 0) issue_y(gnext);
-            if (!(LOAD_X || LOAD_Z)) bulk_wait_read();            // the next epilogue writes these buffers again
+            if (!DX && !(LOAD_X || LOAD_Z)) bulk_wait_read();     // the next epilogue writes these buffers again
         }
         __syncwarp();
         g = gnext;
     }
-    if (lane == 0) bulk_wait_all();
+    if (!DX && lane == 0) bulk_wait_all();
 }
 
 // Stand-alone producer of an exchange (the state came from the host, or Mult was called on a foreign vector): the traces of

@@ -8,13 +8,12 @@
 //   maxwell::B200RK4Solver : mfem::ODESolver                  drop-in for mfem::RK4Solver (linalg/ode.cpp:109-136) as
 //        chosen by Solver::assignODESolver (src/solver/Solver.cpp:41-47): Step(x, t, dt) advances the HOST vector x.
 //        With a B200Evolution underneath the four stages run fused on the device (4 launches, no k vector, no AXPYs);
-//        with any other operator it falls back to the textbook stages through f->Mult, so it can replace RK4Solver
-//        unconditionally.
+//        any other operator is handed to an owned mfem::RK4Solver, so it can replace RK4Solver unconditionally.
 //
 // Header-only, depends on <mfem.hpp> and include/dgtd_b200.h only (serial or parallel MFEM: it takes the
 // mfem::FiniteElementSpace base that ParFiniteElementSpace derives from).  Errors become std::runtime_error like the
-// reference's (src/solver/Solver.cpp:37, 74).  The reference-tree adaptor that fills B200Problem from
-// maxwell::Model / SourcesManager / EvolutionOptions is shown in INTEGRATION.md.
+// reference's (src/solver/Solver.cpp:37, 74).  B200Adaptor.h fills B200Problem from the reference's own
+// maxwell::Model / SourcesManager / EvolutionOptions and adds the constructor with the reference's signature.
 #pragma once
 #include <mfem.hpp>
 
@@ -44,10 +43,16 @@ struct B200Problem {
 
 class B200Evolution : public mfem::TimeDependentOperator {
 public:
-    B200Evolution(mfem::FiniteElementSpace &fes, const B200Problem &pb)
-        : mfem::TimeDependentOperator(6 * fes.GetNDofs()), fes_(fes)   // GlobalEvolution.cpp:34
+    // fes: the space the reference hands to its operators (GlobalEvolution.h:19-22) — on one rank a FiniteElementSpace on the
+    // whole mesh; in the MPI build the rank's ParFiniteElementSpace, and then `serialMesh` is the undivided mesh every rank
+    // holds (Model::getSerialMesh, Model.h:131) together with pb.partitioning, the array the ParMesh was built from
+    // (driver.cpp:1269-1277).  Vectors are sized like the reference's: 6 * fes.GetNDofs() (the rank's own dofs).
+    B200Evolution(mfem::FiniteElementSpace &fes, const B200Problem &pb, mfem::Mesh *serialMesh = nullptr)
+        : mfem::TimeDependentOperator(6 * fes.GetNDofs()), fes_(fes), parlocal_(pb.nranks > 1)   // GlobalEvolution.cpp:34
     {
-        mfem::Mesh &m = *fes.GetMesh();
+        if (pb.nranks > 1 && (!serialMesh || !pb.partitioning))
+            throw std::runtime_error("B200Evolution: a multi-rank operator needs the serial mesh and the partitioning.");
+        mfem::Mesh &m = serialMesh ? *serialMesh : *fes.GetMesh();
         const int dim = m.Dimension(), nv = m.GetNV(), ne = m.GetNE(), nbe = m.GetNBE();
         std::vector<double> verts(3 * (size_t)nv, 0.0);
         for (int v = 0; v < nv; v++) for (int c = 0; c < m.SpaceDimension(); c++) verts[3 * (size_t)v + c] = m.GetVertex(v)[c];
@@ -76,12 +81,13 @@ public:
         o.n_mat = (int)ma.size(); o.mat_attr = ma.data(); o.mat_eps_mu_sigma = mv.data();
         o.pw = pb.planewave; o.tfsf_gate = pb.tfsfGate ? 1 : 0; o.device = pb.device;
         o.rank = pb.rank; o.nranks = pb.nranks; o.partitioning = pb.partitioning;
-        const int rc = dgtd_create(mesh_, &o, &ctx_);
-        if (rc != DGTD_OK) { std::string msg = dgtd_last_error(); dgtd_mesh_destroy(mesh_); mesh_ = nullptr; throw std::runtime_error("B200Evolution: " + msg); }
-        long long n = 0; int np = 0;
-        check(dgtd_sizes(ctx_, &n, &np, nullptr, nullptr));
-        if (6 * n != Height() || np != fes.GetFE(0)->GetDof())
-            throw std::runtime_error("B200Evolution: the finite element space is not the order-p L2 Gauss-Lobatto space the kernels assume.");
+        // a constructor that throws does not run the destructor: release what exists before leaving
+        auto bail = [&](const std::string &msg) { dgtd_destroy(ctx_); ctx_ = nullptr; dgtd_mesh_destroy(mesh_); mesh_ = nullptr; throw std::runtime_error("B200Evolution: " + msg); };
+        if (dgtd_create(mesh_, &o, &ctx_) != DGTD_OK) bail(dgtd_last_error());
+        long long n = 0, nl = 0; int np = 0;
+        if (dgtd_sizes(ctx_, &n, &np, nullptr, &nl) != DGTD_OK) bail(dgtd_last_error());
+        if (6 * (parlocal_ ? nl : n) != Height() || np != fes.GetFE(0)->GetDof())
+            bail("the finite element space is not the order-p L2 Gauss-Lobatto space the kernels assume.");
     }
     ~B200Evolution() override { dgtd_destroy(ctx_); dgtd_mesh_destroy(mesh_); }
     B200Evolution(const B200Evolution &) = delete;
@@ -92,7 +98,15 @@ public:
     {
         if (in.Size() != Height()) throw std::runtime_error("B200Evolution::Mult: input size does not match 6*NDofs.");
         if (out.Size() != Height()) out.SetSize(Height());
-        check(dgtd_mult(ctx_, GetTime(), in.HostRead(), out.HostWrite(), 0));
+        if (parlocal_) check(dgtd_mult_parlocal(ctx_, GetTime(), in.HostRead(), out.HostWrite()));
+        else check(dgtd_mult(ctx_, GetTime(), in.HostRead(), out.HostWrite(), 0));
+    }
+    // host state vectors sized like the reference's Fields::allDOFs on this rank (6 * fes.GetNDofs())
+    void setState(const mfem::Vector &x) const { check(parlocal_ ? dgtd_set_state_parlocal(ctx_, x.HostRead()) : dgtd_set_state(ctx_, x.HostRead())); }
+    void getState(mfem::Vector &x) const
+    {
+        if (x.Size() != Height()) x.SetSize(Height());
+        check(parlocal_ ? dgtd_get_state_parlocal(ctx_, x.HostWrite()) : dgtd_get_state(ctx_, x.HostWrite()));
     }
 
     dgtd_ctx *context() const { return ctx_; }
@@ -104,6 +118,7 @@ public:
 
 private:
     mfem::FiniteElementSpace &fes_;
+    bool parlocal_ = false;               // multi-rank: vectors hold this rank's dofs in its ParMesh's element order
     dgtd_mesh *mesh_ = nullptr;
     dgtd_ctx *ctx_ = nullptr;
 };
@@ -144,21 +159,21 @@ public:
         mfem::ODESolver::Init(f);
         b200_ = dynamic_cast<B200Evolution *>(&f);
         resident_ = false;
-        if (!b200_) { const int n = f.Width(); y_.SetSize(n); k_.SetSize(n); z_.SetSize(n); }
+        if (!b200_) generic_.Init(f);     // any other operator: MFEM's own RK4Solver does the work
     }
     // mfem::ODESolver contract: x is a host vector; it is uploaded, advanced by one fused RK4 step and downloaded.
     void Step(mfem::Vector &x, mfem::real_t &t, mfem::real_t &dt) override
     {
-        if (!b200_) { genericStep(x, t, dt); return; }
-        B200Evolution::check(dgtd_set_state(b200_->context(), x.HostRead()));
+        if (!b200_) { generic_.Step(x, t, dt); return; }
+        b200_->setState(x);
         B200Evolution::check(dgtd_rk4_step(b200_->context(), t, dt));
-        B200Evolution::check(dgtd_get_state(b200_->context(), x.HostWrite()));
+        b200_->getState(x);
         t += dt;
         resident_ = true;
     }
     // Device-resident time loop (Solver::run body without the per-step host touches): upload once, run
     // nsteps, download when a probe/export is due.
-    void Upload(const mfem::Vector &x) { need(); B200Evolution::check(dgtd_set_state(b200_->context(), x.HostRead())); resident_ = true; }
+    void Upload(const mfem::Vector &x) { need(); b200_->setState(x); resident_ = true; }
     void Run(mfem::real_t &t, mfem::real_t dt, int nsteps)
     {
         need(); if (!resident_) throw std::runtime_error("B200RK4Solver::Run: call Upload first.");
@@ -175,25 +190,13 @@ public:
         t = tt;
         return unstable == 0;
     }
-    void Download(mfem::Vector &x) { need(); if (x.Size() != b200_->Height()) x.SetSize(b200_->Height()); B200Evolution::check(dgtd_get_state(b200_->context(), x.HostWrite())); }
+    void Download(mfem::Vector &x) { need(); b200_->getState(x); }
 
 private:
     void need() const { if (!b200_) throw std::runtime_error("B200RK4Solver: the operator is not a B200Evolution."); }
-    void genericStep(mfem::Vector &x, mfem::real_t &t, mfem::real_t &dt)   // ode.cpp:109-136, for foreign operators
-    {
-        f->SetTime(t); f->Mult(x, k_);
-        add(x, dt / 2, k_, y_); add(x, dt / 6, k_, z_);
-        f->SetTime(t + dt / 2); f->Mult(y_, k_);
-        add(x, dt / 2, k_, y_); z_.Add(dt / 3, k_);
-        f->Mult(y_, k_);
-        add(x, dt, k_, y_); z_.Add(dt / 3, k_);
-        f->SetTime(t + dt); f->Mult(y_, k_);
-        add(z_, dt / 6, k_, x);
-        t += dt;
-    }
     B200Evolution *b200_ = nullptr;
     bool resident_ = false;
-    mfem::Vector y_, k_, z_;
+    mfem::RK4Solver generic_;
 };
 
 }  // namespace maxwell

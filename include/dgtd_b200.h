@@ -124,6 +124,13 @@ int  dgtd_get_state(dgtd_ctx *, double *host_6N);
 /* the same with LOCAL host vectors [6][n_local] in this rank's element order (dgtd_local_elements)  */
 int  dgtd_set_state_local(dgtd_ctx *, const double *host_6nlocal);
 int  dgtd_get_state_local(dgtd_ctx *, double *host_6nlocal);
+/* the same with LOCAL host vectors [6][n_local] in the element order of the rank's mfem::ParMesh — the owned elements by
+ * ascending global id, which is what a ParFiniteElementSpace-sized mfem::Vector holds in the reference's MPI build
+ * (Model.cpp:59 builds the ParMesh from the serial mesh and the partitioning).  dgtd_mult_parlocal is
+ * TimeDependentOperator::Mult on such vectors (src/evolution/GlobalEvolution.cpp:628 works on fes_.GetNDofs() local dofs). */
+int  dgtd_set_state_parlocal(dgtd_ctx *, const double *host_6nlocal);
+int  dgtd_get_state_parlocal(dgtd_ctx *, double *host_6nlocal);
+int  dgtd_mult_parlocal(dgtd_ctx *, double t, const double *in_6nlocal, double *out_6nlocal);
 /* device-resident state of this rank in the kernels' NATIVE layout: tetrahedra of order <= 4 use the "aos" layout
  * offset(e, n, c) = (e * Np + n) * 6 + c over local elements in Morton order, n = device node id ("wg_dev2ref" of
  * dgtd_setup_query maps it to the reference node), padded to whole groups of 8 elements; everything else [6][n_local].

@@ -960,7 +960,70 @@ static int cmdKnown(const std::string &path, const std::string &meshFile)
 // its own operator — mfem::TimeDependentOperator::Mult, mfem::RK4Solver::Step — next to the reference-based GlobalOracle
 // on the same mfem::FiniteElementSpace.  Needs a GPU (the product has no CPU path); this binary is the checker.
 // ----------------------------------------------------------------------------
-#include "B200Evolution.h"
+#include "B200Adaptor.h"
+// Stand-ins for the reference's Model / SourcesManager / EvolutionOptions with the SAME accessor names and value types
+// (src/components/Model.h:131-156, Material.h:51-53, src/solver/SourcesManager.h:34, src/components/Sources.h,
+// src/math/Function.h:47-136, 328-409, src/evolution/EvolutionOptions.h:13-20, src/components/Types.h:48-56): the real
+// classes need MPI (Model owns a ParMesh), which this image lacks, so the adaptor template is instantiated on these.
+namespace mock {
+enum class BdrCond { PEC, PMC, SMA, SurfaceCond, NearToFarField = 201, TotalFieldIn = 301, SGBC = 401 };
+enum FieldType { E = 0, H = 1 };
+struct Material
+{
+   double eps, mu, sigma;
+   double getPermittivity() const { return eps; }
+   double getPermeability() const { return mu; }
+   double getConductivity() const { return sigma; }
+};
+struct Function { virtual ~Function() = default; };
+struct Gaussian : Function
+{
+   double spread_; Vector mean_;
+   Gaussian(double s, double m) : spread_(s), mean_(1) { mean_[0] = m; }
+   double spread() const { return spread_; }
+   const Vector &mean() const { return mean_; }
+};
+struct ModulatedGaussian : Function
+{
+   double spread_, freq_; Vector mean_;
+   ModulatedGaussian(double s, double m, double f) : spread_(s), freq_(f), mean_(1) { mean_[0] = m; }
+   double spread() const { return spread_; }
+   const Vector &mean() const { return mean_; }
+   double frequency() const { return freq_; }
+};
+struct EHFieldFunction { virtual ~EHFieldFunction() = default; };
+struct Planewave : EHFieldFunction
+{
+   std::unique_ptr<Function> function_; Vector polarization_, propagation_; FieldType fieldtype_;
+   Function *function() { return function_.get(); }
+   const Vector &polarization() const { return polarization_; }
+   const Vector &propagation() const { return propagation_; }
+   FieldType fieldType() const { return fieldtype_; }
+};
+struct Source { virtual ~Source() = default; };
+struct InitialField : Source {};
+struct TotalField : Source
+{
+   std::unique_ptr<EHFieldFunction> function_;
+   EHFieldFunction *function() { return function_.get(); }
+};
+struct SourcesManager { std::vector<std::unique_ptr<Source>> sources; };
+struct EvolutionOptions { int op = 1; int order = 2; double alpha = 1.0; };   // EvolutionOperatorType::Global = 1
+struct Model
+{
+   Mesh &mesh;
+   std::map<int, BdrCond> bdr, intBdr;
+   std::map<int, Material> mat;
+   std::map<BdrCond, Array<int>> tfsf;
+   explicit Model(Mesh &m) : mesh(m) {}
+   const std::map<int, BdrCond> &getGeomTagToBoundaryCond() const { return bdr; }
+   const std::map<int, BdrCond> &getGeomTagToIntBoundaryCond() const { return intBdr; }
+   const std::map<int, Material> &getGeomTagToMaterial() const { return mat; }
+   std::map<BdrCond, Array<int>> &getTotalFieldScatteredFieldToMarker() { return tfsf; }
+   Mesh &getSerialMesh() { return mesh; }
+};
+using Types = maxwell::B200SourceTypes<TotalField, Planewave, Gaussian, ModulatedGaussian>;
+}  // namespace mock
 static double relL2(const Vector &a, const Vector &b)
 {
    Vector d(a); d -= b; double nb = b.Norml2(); return d.Norml2() / (nb > 0 ? nb : 1.0);
@@ -978,17 +1041,41 @@ static int cmdShell(std::map<std::string, std::string> &a)
    std::vector<double> xyz; nodeCoords(fes, xyz);
    op.pw = pd.pw;
    if (!pd.tfsf_tags.empty()) { op.Atfsf = buildTFSF(F); op.src = buildTFSFSource(F, xyz); }
-   maxwell::B200Problem bp;
-   bp.order = pd.order; bp.alpha = pd.alpha;
-   for (auto &kv : pd.bdr) { bp.bdr[kv.first] = kv.second == BC_PEC ? DGTD_BC_PEC : kv.second == BC_PMC ? DGTD_BC_PMC : DGTD_BC_SMA; }
-   bp.tfsfTags = pd.tfsf_tags; bp.materials = pd.mat;
-   if (pd.pw.on)
+   // the reference's objects as its driver would fill them (driver.cpp:1012-1041 splits the boundary tags into true and
+   // interior ones; buildGaussianPlanewave / buildModulatedGaussianPlanewave, driver.cpp:483-519)
+   mock::Model model(mesh);
+   mock::SourcesManager srcs;
+   mock::EvolutionOptions eo; eo.order = pd.order; eo.alpha = pd.alpha; eo.op = 1;
    {
-      bp.planewave.enabled = 1; bp.planewave.spread = pd.pw.spread; bp.planewave.mean1d = pd.pw.mean1d; bp.planewave.freq = pd.pw.freq;
-      for (int d = 0; d < 3; d++) { bp.planewave.pol[d] = pd.pw.pol[d]; bp.planewave.dir[d] = pd.pw.dir[d]; }
-      bp.planewave.fieldtype = pd.pw.fieldtype;
+      std::set<int> interiorTag;
+      for (int be = 0; be < mesh.GetNBE(); be++)
+         if (pd.bdr.count(mesh.GetBdrAttribute(be)) && mesh.FaceIsInterior(mesh.GetBdrElementFaceIndex(be))) { interiorTag.insert(mesh.GetBdrAttribute(be)); }
+      for (auto &kv : pd.bdr)
+      {
+         mock::BdrCond c = kv.second == BC_PEC ? mock::BdrCond::PEC : kv.second == BC_PMC ? mock::BdrCond::PMC : mock::BdrCond::SMA;
+         (interiorTag.count(kv.first) ? model.intBdr : model.bdr)[kv.first] = c;
+      }
+      for (auto &kv : pd.mat) { model.mat[kv.first] = mock::Material{kv.second[0], kv.second[1], kv.second[2]}; }
+      if (!pd.tfsf_tags.empty())
+      {
+         Array<int> mk(mesh.bdr_attributes.Max()); mk = 0;
+         for (int t : pd.tfsf_tags) { mk[t - 1] = 1; }
+         model.tfsf[mock::BdrCond::TotalFieldIn] = mk;
+      }
+      if (pd.pw.on)
+      {
+         auto pw = std::make_unique<mock::Planewave>();
+         if (pd.pw.freq == 0.0) { pw->function_ = std::make_unique<mock::Gaussian>(pd.pw.spread, pd.pw.mean1d); }
+         else { pw->function_ = std::make_unique<mock::ModulatedGaussian>(pd.pw.spread, pd.pw.mean1d, pd.pw.freq); }
+         pw->polarization_.SetSize(3); pw->propagation_.SetSize(3);
+         for (int d = 0; d < 3; d++) { pw->polarization_[d] = pd.pw.pol[d]; pw->propagation_[d] = pd.pw.dir[d]; }
+         pw->fieldtype_ = pd.pw.fieldtype == FE ? mock::E : mock::H;
+         auto tf = std::make_unique<mock::TotalField>(); tf->function_ = std::move(pw);
+         srcs.sources.push_back(std::make_unique<mock::InitialField>());
+         srcs.sources.push_back(std::move(tf));
+      }
    }
-   maxwell::B200Evolution ev(fes, bp);
+   maxwell::B200EvolutionFor<mock::Types> ev(fes, model, srcs, eo);      // the reference's constructor signature
    const double dt = a.count("dt") ? std::stod(a["dt"]) : 1e-3;
    const int steps = a.count("steps") ? std::stoi(a["steps"]) : 3;
    const double t0 = a.count("t0") ? std::stod(a["t0"]) : 0.0;
