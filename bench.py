@@ -349,6 +349,7 @@ def main():
     ap.add_argument("--sustain-s", type=float, default=2.0, help="length of the sustained window in seconds (0: skip)")
     ap.add_argument("--parity-steps", type=int, default=5, help="N > 1: steps of the N-rank vs 1-rank comparison (0: skip)")
     ap.add_argument("--no-gate", action="store_true", help="N > 1: skip the small-fixture parity gate")
+    ap.add_argument("--parity-report-only", action="store_true", help="N > 1: report the bench-size parity instead of aborting on it (debugging)")
     args = ap.parse_args()
     if args.order is None:
         args.order = 4 if args.workload == "c4" else 3
@@ -463,7 +464,7 @@ def main():
         parity.update({"bench_size_rel_l2_max_over_ranks": allmax(rel_rank), "bench_size_rel_l2_global": math.sqrt(float(tot[0]) / float(tot[1])),
                        "bench_size_steps": args.parity_steps, "bench_size_dofs": 6 * N,
                        "how": "owned DOFs of every rank after the same steps of the same global mesh on rank 0's GPU alone"})
-        if not (parity["bench_size_rel_l2_max_over_ranks"] <= PARITY_TOL):
+        if not (parity["bench_size_rel_l2_max_over_ranks"] <= PARITY_TOL) and not args.parity_report_only:
             if rank == 0:
                 print(json.dumps({"error": "multi-GPU parity at the bench size failed", "parity": parity}))
             ev.close()

@@ -118,20 +118,10 @@ static KernelSet select_kernels(int dim, int p)
 // the warp-per-group kernel: tetrahedra of order 1..4, element-major "aos" layout, one warp per group of 8 elements
 typedef void (*WgFn)(const WgArgs);
 struct WgSet { WgFn fn[4]; int threads; size_t smem; };
-template <int P, bool TF, bool DX = false> static WgSet wgset()
+template <int P, bool TF, bool TWO = false> static WgSet wgset()
 {
-    using B = Wg<P, DX>;
-    return {{stage_wg_kernel<P, 0, TF, DX>, stage_wg_kernel<P, 1, TF, DX>, stage_wg_kernel<P, 2, TF, DX>, stage_wg_kernel<P, 3, TF, DX>}, B::T, B::smem_bytes};
-}
-// the same kernel with x / z through direct global accesses (kernels_wg.cuh: DX): 12 instead of 8 warps per SM at order <= 3
-static bool select_wgx(int dim, int p, bool tf, WgSet &ws)
-{
-    if (dim != 3) return false;
-    switch (p) {
-        case 1: ws = tf ? wgset<1, true, true>() : wgset<1, false, true>(); return true; case 2: ws = tf ? wgset<2, true, true>() : wgset<2, false, true>(); return true;
-        case 3: ws = tf ? wgset<3, true, true>() : wgset<3, false, true>(); return true; case 4: ws = tf ? wgset<4, true, true>() : wgset<4, false, true>(); return true;
-    }
-    return false;
+    using B = Wg<P, TWO>;
+    return {{stage_wg_kernel<P, 0, TF, TWO>, stage_wg_kernel<P, 1, TF, TWO>, stage_wg_kernel<P, 2, TF, TWO>, stage_wg_kernel<P, 3, TF, TWO>}, B::T, B::smem_bytes};
 }
 // tf = the context injects a TF/SF plane wave
 static bool select_wg(int dim, int p, bool tf, WgSet &ws)
@@ -140,6 +130,17 @@ static bool select_wg(int dim, int p, bool tf, WgSet &ws)
     switch (p) {
         case 1: ws = tf ? wgset<1, true>() : wgset<1, false>(); return true; case 2: ws = tf ? wgset<2, true>() : wgset<2, false>(); return true;
         case 3: ws = tf ? wgset<3, true>() : wgset<3, false>(); return true; case 4: ws = tf ? wgset<4, true>() : wgset<4, false>(); return true;
+    }
+    return false;
+}
+// the same kernel with two instead of three group buffers per warp (kernels_wg.cuh: TWO): 12 instead of 8 warps per SM at
+// order <= 3; not for contexts with conductivity
+static bool select_wg2(int dim, int p, bool tf, WgSet &ws)
+{
+    if (dim != 3) return false;
+    switch (p) {
+        case 1: ws = tf ? wgset<1, true, true>() : wgset<1, false, true>(); return true; case 2: ws = tf ? wgset<2, true, true>() : wgset<2, false, true>(); return true;
+        case 3: ws = tf ? wgset<3, true, true>() : wgset<3, false, true>(); return true; case 4: ws = tf ? wgset<4, true, true>() : wgset<4, false, true>(); return true;
     }
     return false;
 }
@@ -166,7 +167,7 @@ struct dgtd_ctx {
     HostOp H;
     WgPlan WP;
     bool has_sigma = false;
-    bool wgx = false;                // ... with x / z through direct global accesses (12 warps per SM)
+    bool wg2 = false;                // ... with two group buffers per warp (12 warps per SM)
     bool wh = false;                 // ... or its half-row form (kernels_wh.cuh, groups of 4 elements); wg stays set: same plan and layout
     int wg_groups_per_cta = 0;
     bool wg = false;                 // aos layout + warp-per-group kernel (the state needs a layout conversion at the ABI)
@@ -199,8 +200,7 @@ struct dgtd_ctx {
     size_t p2p_peer_hb[P2P_MAXPEERS] = {};
     unsigned long long epoch = 0;                    // exchanges produced so far (all ranks run the same sequence)
     const double *pushed = nullptr;                  // vector whose traces exchange `epoch` carries (nullptr: none valid)
-    DevBuf<unsigned int> p2p_done, p2p_cnt;         // last-CTA election of the stand-alone push kernel; per-peer arrival counters of the fused push
-    DevBuf<int> worder;                              // WgPlan::order (multi-rank contexts: partition-face groups first)
+    DevBuf<unsigned int> p2p_done;
     DevBuf<int> p2p_err;
     DevBuf<int> hpush, dgid, dlidx;                  // dgid: local element -> caller's element index (H.elem_gid); dlidx: -> its rank among the owned elements by global id
     long long launches = 0;
@@ -266,9 +266,8 @@ static void p2p_setup(dgtd_ctx *c)
         c->p2p_hb = (((size_t)c->H.n_halo_faces * c->H.Nfp * 6 * sizeof(double)) + 127) / 128 * 128;
         c->p2p_mem.alloc(4096 + 2 * c->p2p_hb + 128);
         CU(cudaMemset(c->p2p_mem.p, 0, c->p2p_mem.n));
-        c->p2p_done.alloc(1); c->p2p_err.alloc(1); c->p2p_cnt.alloc(P2P_MAXPEERS);
+        c->p2p_done.alloc(1); c->p2p_err.alloc(1);
         CU(cudaMemset(c->p2p_done.p, 0, sizeof(unsigned int))); CU(cudaMemset(c->p2p_err.p, 0, sizeof(int)));
-        CU(cudaMemset(c->p2p_cnt.p, 0, P2P_MAXPEERS * sizeof(unsigned int)));
         if (cudaIpcGetMemHandle(&mine.h, c->p2p_mem.p) != cudaSuccess) { cudaGetLastError(); want = 0; }
         mine.hb = c->p2p_hb;
     }
@@ -341,8 +340,7 @@ static WgP2P p2p_args(dgtd_ctx *c, unsigned long long wait, unsigned long long s
         q.peer_flag[p] = reinterpret_cast<unsigned long long *>(base) + c->H.peers[p].remote_idx;
     }
     q.wait_epoch = wait; q.signal_epoch = signal;
-    q.done = c->p2p_done.p; q.cnt = c->p2p_cnt.p; q.err = c->p2p_err.p;
-    for (int p = 0; p < q.npeers; p++) q.need[p] = c->wh ? c->WP.need4[(size_t)p] : c->WP.need8[(size_t)p];
+    q.done = c->p2p_done.p; q.err = c->p2p_err.p;
     return q;
 }
 static const double *p2p_halo_in(dgtd_ctx *c, unsigned long long k)
@@ -372,7 +370,6 @@ static void launch_stage(dgtd_ctx *c, int mode, StageArgs &A)
         }
         W.bfrag = c->bafrag.p; W.geo = c->bgeo.p; W.desc = c->bdesc.p; W.tab = c->wtab.p; W.ntab = c->WP.ntab;
         W.tfsf_xyz = A.tfsf_xyz; W.gate = A.gate; W.halo = A.halo; W.ngroups = c->WP.ngroups; W.has_sigma = c->has_sigma ? 1 : 0;
-        W.order = c->nranks > 1 ? c->worder.p : nullptr;
         W.alpha = A.alpha; W.pw = A.pw; W.pw_on = A.pw_on;
         W.yin = A.yin; W.x = A.x; W.z = A.z; W.yout = A.yout; W.a = A.a; W.b = A.b; W.t = A.t;
         c->wgs.fn[mode]<<<c->grid, c->wgs.threads, c->wgs.smem, c->stream>>>(W);
@@ -614,10 +611,10 @@ int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
         c->WP = build_wg_plan(H);
         if (c->WP.ntab <= Wg<3>::TABROWS) c->wg = c->wh = true;
     }
-    if (!c->wg && ksel == "wgx" && select_wgx(H.dim, H.p, has_tf, c->wgs) && c->wgs.smem <= (size_t)prop.sharedMemPerBlockOptin) {
+    if (!c->wg && ksel == "wg2" && !has_sigma && select_wg2(H.dim, H.p, has_tf, c->wgs) && c->wgs.smem <= (size_t)prop.sharedMemPerBlockOptin) {
         c->WP = build_wg_plan(H);
         c->wg_groups_per_cta = c->wgs.threads / 32;
-        if (c->WP.ntab <= Wg<3>::TABROWS) c->wg = c->wgx = true;
+        if (c->WP.ntab <= Wg<3>::TABROWS) c->wg = c->wg2 = true;
     }
     if (!c->wg && (ksel == "wg" || ksel == "wh" || ksel.empty()) && select_wg(H.dim, H.p, has_tf, c->wgs) && c->wgs.smem <= (size_t)prop.sharedMemPerBlockOptin) {
         c->WP = build_wg_plan(H);
@@ -632,7 +629,6 @@ int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
         c->grid = (int)std::min<long long>((units + nw - 1) / nw, (long long)prop.multiProcessorCount);
         c->bgeo.upload(c->WP.geo); c->bafrag.upload(c->WP.bfrag); c->bdesc.upload(c->WP.desc); c->bsend_off.upload(c->WP.send_off, 1);
         c->wtab.upload(c->WP.tab, 16); c->dev2ref.upload(c->WP.dev2ref); c->hpush.upload(c->WP.hpush, 2);
-        if (c->nranks > 1) c->worder.upload(c->WP.order, 1);
     } else {
         if (H.ntab > 256) throw Error(DGTD_ERR_UNSUPPORTED, "too many distinct face orientations for the generic kernel");
         c->Nalloc = c->Nloc;
@@ -1031,7 +1027,7 @@ int dgtd_kernel_info(const dgtd_ctx *c, char *buf, int cap)
                       c->H.p, c->wgs.threads, c->wgs.smem, c->grid, c->nranks == 1 ? "" : c->p2p ? ", halo: fused peer-memory stores" : ", halo: NCCL send/recv");
     else if (c->wg)
         std::snprintf(tmp, sizeof tmp, "stage_wg_kernel<P=%d,MODE%s> DMMA m8n8k4 transposed, warp per group of 8 elements, aos layout%s, %d threads, %zu B smem, grid %d%s",
-                      c->H.p, c->wgx ? ",DX" : "", c->wgx ? ", x/z by direct global accesses" : "", c->wgs.threads, c->wgs.smem, c->grid,
+                      c->H.p, c->wg2 ? ",TWO" : "", c->wg2 ? ", 2 group buffers per warp" : "", c->wgs.threads, c->wgs.smem, c->grid,
                       c->nranks == 1 ? "" : c->p2p ? ", halo: fused peer-memory stores" : ", halo: NCCL send/recv");
     else
         std::snprintf(tmp, sizeof tmp, "stage_kernel<DIM=%d,P=%d,MODE> generic, %d threads, %zu B smem, grid %d", c->H.dim, c->H.p, c->ks.threads, c->ks.smem, c->grid);
@@ -1076,8 +1072,6 @@ int dgtd_setup_query(const dgtd_mesh *mesh, const dgtd_options *o, const char *n
         else if (n == "wg_desc") { src = WP.desc.data(); bytes = WP.desc.size() * 4; }
         else if (n == "wg_send_off") { src = WP.send_off.data(); bytes = WP.send_off.size() * 8; }
         else if (n == "wg_dev2ref") { src = WP.dev2ref.data(); bytes = WP.dev2ref.size() * 4; }
-        else if (n == "wg_order") { src = WP.order.data(); bytes = WP.order.size() * 4; }
-        else if (n == "wg_need") { dims = WP.need8; dims.insert(dims.end(), WP.need4.begin(), WP.need4.end()); dims.push_back(WP.nfront); src = dims.data(); bytes = dims.size() * 4; }
         else throw Error(DGTD_ERR_ARG, "unknown setup table " + n);
     }
     else if (n == "dims") { dims = {H.dim, H.p, H.Np, H.Nfp, H.nf, H.NEloc, H.ntab, H.n_tfsf_faces, H.n_halo_faces}; src = dims.data(); bytes = dims.size() * 4; }

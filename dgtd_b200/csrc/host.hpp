@@ -115,11 +115,12 @@ constexpr int BLK_E = 8;               // elements per group (= DMMA m dimension
 // id (dev2ref maps it to the reference node); 8 consecutive local elements form a group = one warp's unit of work, one
 // contiguous chunk of Np*8*6 doubles.  The contraction runs "transposed" (DMMA A = data [8 elements x 4 nodes],
 // B = operator [4 nodes x 8 output nodes]) so that a lane owns one element through all phases.
-// geometry record of the wg / wh kernels, 26 doubles: J / det J (dx_d/dxi_a at 3d+a), Jinv[9] (dxi_a/dx_d at 9+3a+d),
-// fscale[4] at 18, 1/det J at 22, det/eps 23, det/mu 24, sigma/eps 25, 1/fscale[4] at 26 — padded to a stride of 34 so that the records of
-// the 8 elements of a group start 4 banks apart in shared memory (a stride of 32 doubles puts them all on the same banks:
-// every geometry LDS.128 cost 8 wavefronts instead of 1)
-constexpr int WG_GEO = 34;
+// geometry record of the wg / wh kernels, 30 doubles: J / det J (dx_d/dxi_a at 3d+a), Jinv[9] (dxi_a/dx_d at 9+3a+d),
+// fscale[4] at 18, 1/det J at 22, det/eps 23, det/mu 24, sigma/eps 25, 1/fscale[4] at 26.  A stride of 30 doubles puts the
+// records of the 8 elements of a group 28 banks apart in shared memory (distinct multiples of 4 banks: conflict-free
+// LDS.128); a stride of 32 would put them all on the same banks, every geometry LDS.128 costing 8 wavefronts instead of 1
+constexpr int WG_GEO = 30;
+constexpr int WG_TABROWS = 72;         // rows of the node tables kept in shared memory (8 own/canonical + neighbour orientations + push rows)
 struct WgPlan {
     int ngroups = 0, NEpad = 0;
     int NT = 0, KSV = 0;               // output n-tiles (the last one is "mixed"), k-steps of the volume contraction
@@ -127,15 +128,12 @@ struct WgPlan {
     std::vector<int> dev2ref, ref2dev; // Np
     std::vector<int> forder;           // 4*Nfp : step s of face f handles canonical face node forder[f*Nfp+s]
     std::vector<double> geo;           // NEpad * WG_GEO
-    std::vector<int> desc;             // NEpad*4*2 : {nbr local element | -1 boundary | -2-haloFace, code (FI_TAB = row of tab; partition faces: peer index)}
+    std::vector<int> desc;             // NEpad*4*2 : {nbr local element | -1 boundary | -2-haloFace, code (FI_TAB = row of tab)}
     std::vector<uint8_t> tab;          // ntab*16 : rows 0..3 own device node per step, 4..7 canonical index per step, 8.. neighbour device node per step
     int ntab = 0;
     std::vector<double> bfrag;         // (nfrag_vol + nfrag_lift) * 32
     std::vector<long long> send_off;   // nSendFaces*Nfp : offset (doubles) of the node record in the aos state
     std::vector<int> hpush;            // nHaloFaces*2 : {peer index | tab row << 8 (own device node per RECEIVER face node), slot on the peer}
-    std::vector<int> order;            // ngroups : processing order of the groups, the nfront groups owning a partition face first
-    int nfront = 0;
-    std::vector<int> need8, need4;     // per peer: groups of 8 / of 4 elements that push traces to it (flag raised by the last one)
 };
 WgPlan build_wg_plan(const HostOp &H);
 void node_coords(const Mesh &m, const RefElem &ref, std::vector<double> &xyz);   // [NE*Np][3], global numbering

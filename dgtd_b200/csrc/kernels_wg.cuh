@@ -27,11 +27,14 @@ namespace dgtd {
 
 // Direct halo exchange over NVLink peer memory (one process per GPU, buffers mapped with CUDA IPC): the stage kernel that
 // PRODUCES y_out stores the traces of its partition faces straight into the neighbour rank's halo buffer, and the kernel
-// that CONSUMES them waits, only in the lanes that own a partition face, for that neighbour's epoch flag.  Exchange number k
-// uses halo buffer k & 1 on every rank.  A rank raises peer p's flag to k after all its stores of exchange k TO p; the
-// groups that store to p are exactly the groups that read p's traces of exchange k-1 (same faces, flux before epilogue), so
-// the flag also says "my reads of your block of exchange k-1 are over" and two buffers are enough.  The groups owning
-// partition faces are processed first in a launch (WgPlan::order), so the flags are up long before the consumer asks.
+// that CONSUMES them waits, only in the warps that own a partition face, for the neighbour's epoch flag.  Exchange number k
+// uses halo buffer k & 1 on every rank; a rank signals k after ALL its stores of exchange k (every CTA fences system-wide,
+// the last CTA of the grid raises the flags), which is also after its reads of exchange k-1, so two buffers are enough
+// (see capi.cu: p2p_* for the host side).
+// Round 2 tried to raise a peer's flag as soon as the last group touching that peer had stored (per-peer arrival counters,
+// partition-face groups first in the launch): correct on the small fixtures, but at 786 K elements per rank the N-rank run
+// differed from the single-GPU run by 1e-8 .. 1e-5 in every variant of the arrival fence, so the flag stays at
+// the end of the launch, where all stores of the grid are ordered before it by one fence per CTA.
 // Replaces GlobalEvolution.cpp:763-774 (six blocking MPI exchanges of whole neighbour elements per Mult).
 constexpr int P2P_MAXPEERS = 8;
 struct WgP2P {
@@ -41,9 +44,7 @@ struct WgP2P {
     const unsigned long long *flags;                     // my flag slots, one per peer
     int npeers;
     unsigned long long wait_epoch, signal_epoch;         // 0: nothing to wait for / nothing to produce
-    unsigned int *cnt;                                   // per-peer arrival counters of the fused push (stage kernels)
-    int need[P2P_MAXPEERS];                              // units (groups) of this launch that push traces to each peer
-    unsigned int *done;                                  // CTA counter of the last-CTA election (stand-alone push kernel)
+    unsigned int *done;                                  // CTA counter of the last-CTA election
     int *err;                                            // set when a wait timed out
 };
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
@@ -62,51 +63,18 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ void p2p_spin(const WgP2P &pp, int peer)
-{
-    const unsigned long long t0 = globaltimer_ns();
-    while (ld_acquire_sys(pp.flags + peer) < pp.wait_epoch) {
-        if (globaltimer_ns() - t0 > 20000000000ull) { atomicExch(pp.err, 1); break; }     // 20 s without progress: give up
-    }
-}
-// lanes 0..npeers-1 of the calling warp wait for their peer's flag (stand-alone push kernel: all peers)
+// lanes 0..npeers-1 of the calling warp wait for their peer's flag; 20 s without progress sets *err and gives up
 __device__ __forceinline__ void p2p_wait(const WgP2P &pp, int lane)
 {
-    if (lane < pp.npeers) p2p_spin(pp, lane);
-    __syncwarp();
-}
-// Consumer side of a stage kernel: a lane that owns a partition face waits for THAT peer's flag (mypeer = -1: no such
-// face); `ready` is the warp-uniform set of peers already seen at wait_epoch, so every peer is polled once per warp.
-__device__ __forceinline__ unsigned p2p_wait_peers(const WgP2P &pp, int mypeer, unsigned ready)
-{
-    const bool must = mypeer >= 0 && !((ready >> mypeer) & 1u);
-    if (__any_sync(0xffffffffu, must)) {
-        if (must) p2p_spin(pp, mypeer);
-        ready |= __reduce_or_sync(0xffffffffu, must ? 1u << mypeer : 0u);
-    }
-    return ready;
-}
-// Producer side of a stage kernel, called by a whole warp after its lanes stored the traces of their partition faces
-// (mypeer = -1: this lane stored nothing): one arrival per distinct peer of the group; the warp that brings a peer's
-// counter to need[peer] raises that peer's flag, i.e. a neighbour is signalled as soon as the LAST unit touching it is done,
-// not at the end of the launch.  The elected lane's system-scope fence is cumulative over the other lanes' stores
-// (ordered before it by the warp barrier), as in a grid barrier (bar; fence; atomic).
-__device__ __forceinline__ void p2p_arrive(const WgP2P &pp, int mypeer, int lane)
-{
-    __syncwarp();
-    const unsigned same = __match_any_sync(0xffffffffu, mypeer);
-    if (mypeer >= 0 && lane == __ffs(same) - 1) {
-        __threadfence_system();
-        const unsigned prev = atomicAdd(pp.cnt + mypeer, 1u);
-        if (prev + 1u == (unsigned)pp.need[mypeer]) {
-            pp.cnt[mypeer] = 0;                          // nobody else arrives for this peer before the next launch
-            __threadfence_system();
-            st_release_sys(pp.peer_flag[mypeer], pp.signal_epoch);
+    if (lane < pp.npeers) {
+        const unsigned long long t0 = globaltimer_ns();
+        while (ld_acquire_sys(pp.flags + lane) < pp.wait_epoch) {
+            if (globaltimer_ns() - t0 > 20000000000ull) { atomicExch(pp.err, 1); break; }
         }
     }
+    __syncwarp();
 }
-// stand-alone push kernel: after the last store of the CTA make them visible system-wide, elect the last CTA of the grid,
-// signal every peer
+// after the last store of the CTA: make them visible system-wide, elect the last CTA of the grid, signal every peer
 __device__ __forceinline__ void p2p_signal(const WgP2P &pp)
 {
     __threadfence_system();
@@ -130,7 +98,6 @@ struct WgArgs {
     const double *tfsf_xyz;
     const double *gate;
     const double *halo;       // [haloFace][Nfp][6]
-    const int *order;         // WgPlan::order (nullptr: groups in memory order)
     int ngroups;
     int has_sigma;
     double alpha;
@@ -142,30 +109,33 @@ struct WgArgs {
     WgP2P pp;
 };
 
-// DX ("direct x/z"): only y_in is staged in shared memory; x and z are read and y_out / z written with per-lane 128-bit
-// global accesses in the epilogue (the four lanes of an element cover 192 contiguous bytes = 6 whole sectors per node slot).
-// A warp then needs 10 KB instead of 25 KB of shared memory, so 12 warps (3 per scheduler) fit at order <= 3 and 8 at order 4
-// instead of 8 / 4: the FP64 pipe idles whenever every warp of a scheduler sits in a load wait or in the epilogue.
-template <int P, bool DX = false> struct Wg {
+// TWO: two group buffers per warp instead of three, so that 12 warps (3 per scheduler) instead of 8 fit on an SM at order
+// <= 3 — the FP64 pipe idles whenever every warp of a scheduler sits in a load wait or in the epilogue (ncu: pipe 73 % busy
+// with 2 warps per scheduler).  Buffer A holds y_in until the flux is done, then x (bulk load after the last read of y_in;
+// stage 1: x IS y_in, nothing to load) and finally y_out in place; buffer B holds z, loaded early, and z_new in place.  The
+// price: the next group's y_in can only be requested once the stores have left buffer A (stage 4 and the 3-buffer kernel
+// request it at the start of the epilogue), and the x load of stages 2-3 is exposed — latencies a third warp covers.
+// Not for contexts with conductivity (the epilogue then reads E of y_in, which buffer A no longer holds).
+template <int P, bool TWO = false> struct Wg {
     static constexpr int Np = (P + 1) * (P + 2) * (P + 3) / 6, Nfp = (P + 1) * (P + 2) / 2;
     static constexpr int NT = (Np + 7) / 8, KSV = (Np + 3) / 4, VT = (NT - 1) * 3 + 3;
 #ifndef DGTD_WG_NW
 #define DGTD_WG_NW 8
 #endif
-#ifndef DGTD_WGX_NW
-#define DGTD_WGX_NW 12
+#ifndef DGTD_WG2_NW
+#define DGTD_WG2_NW 12
 #endif
-    static constexpr int NW = DX ? (P <= 3 ? DGTD_WGX_NW : 8) : (P <= 3 ? DGTD_WG_NW : 4), T = 32 * NW;   // warps per CTA = groups in flight per SM
+    static constexpr int NW = TWO ? (P <= 3 ? DGTD_WG2_NW : 6) : (P <= 3 ? DGTD_WG_NW : 4), T = 32 * NW;   // warps per CTA = groups in flight per SM
     static constexpr int GS = Np * BLK_E * 6;                    // doubles per group of one state vector
     static constexpr int NFV = KSV * VT, NFL = Nfp * NT, NFR = NFV + NFL;
     static constexpr int WGEO = BLK_E * WG_GEO, WDESC = BLK_E * 4 * 2;   // doubles / ints per group
-    static constexpr int NBUF = DX ? 1 : 3;                      // group buffers per warp: Y [, X, Z]
+    static constexpr int NBUF = TWO ? 2 : 3;                     // group buffers per warp
     static constexpr int WDBL = NBUF * GS + WGEO + WDESC / 2;    // doubles per warp: buffers, geometry, descriptors
-    static constexpr int TABROWS = 136;
+    static constexpr int TABROWS = WG_TABROWS;
     static constexpr int oWarp = NFR * 32;
     static constexpr size_t bTab = (size_t)(oWarp + NW * WDBL) * 8;
     static constexpr size_t bBar = bTab + (size_t)TABROWS * 16;
-    static constexpr size_t smem_bytes = bBar + (size_t)(NW * 2 + 1) * 8;     // per-warp barriers + one for the operator fragments
+    static constexpr size_t smem_bytes = bBar + (size_t)(NW * 3 + 1) * 8;     // per-warp barriers (y, x, z) + one for the operator fragments
     static_assert(Np - 8 * (NT - 1) <= 4, "mixed last tile");
     static_assert((GS % 2) == 0 && (bTab % 16) == 0, "alignment");
 };
@@ -195,22 +165,6 @@ __device__ __forceinline__ void load_rec_split(const double *p, bool in_smem, do
                      : "=d"(u[0]), "=d"(u[1]), "=d"(u[2]), "=d"(u[3]), "=d"(u[4]), "=d"(u[5]) : "l"(p));
     }
 }
-__device__ __forceinline__ void load_rec_global(const double *p, double *u)
-{
-    asm volatile("ld.global.v2.f64 {%0,%1}, [%6];\n\tld.global.v2.f64 {%2,%3}, [%6+16];\n\tld.global.v2.f64 {%4,%5}, [%6+32];"
-                 : "=d"(u[0]), "=d"(u[1]), "=d"(u[2]), "=d"(u[3]), "=d"(u[4]), "=d"(u[5]) : "l"(p));
-}
-// records another lane of this warp has just written (after __syncwarp): L2, not a possibly stale L1 line
-__device__ __forceinline__ void load_rec_global_cg(const double *p, double *u)
-{
-    asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%6];\n\tld.global.cg.v2.f64 {%2,%3}, [%6+16];\n\tld.global.cg.v2.f64 {%4,%5}, [%6+32];"
-                 : "=d"(u[0]), "=d"(u[1]), "=d"(u[2]), "=d"(u[3]), "=d"(u[4]), "=d"(u[5]) : "l"(p) : "memory");
-}
-__device__ __forceinline__ void store_rec_global(double *p, const double *u)
-{
-    asm volatile("st.global.v2.f64 [%0], {%1,%2};\n\tst.global.v2.f64 [%0+16], {%3,%4};\n\tst.global.v2.f64 [%0+32], {%5,%6};"
-                 ::"l"(p), "d"(u[0]), "d"(u[1]), "d"(u[2]), "d"(u[3]), "d"(u[4]), "d"(u[5]) : "memory");
-}
 __device__ __forceinline__ void store_rec(double *p, const double *u)
 {
     double2 *q = reinterpret_cast<double2 *>(p);
@@ -223,50 +177,53 @@ __device__ __forceinline__ void store_rec(double *p, const double *u)
 // Measured alternatives (profiles/): one-step prefetch issued inside the face loop with the flux in physical
 // components, 97.9 G vs 110 G; asm-volatile (pinned) prefetch loads, +-0; prefetch.global.L1 of the records, -9 %.
 // TF: the context has a TF/SF plane-wave source (the injection code sits in the face loop only then).
-template <int P, int MODE, bool TF, bool DX>
-__global__ void __launch_bounds__(Wg<P, DX>::T, 1) stage_wg_kernel(const WgArgs A)
+template <int P, int MODE, bool TF, bool TWO>
+__global__ void __launch_bounds__(Wg<P, TWO>::T, 1) stage_wg_kernel(const WgArgs A)
 {
-    using B = Wg<P, DX>;
+    using B = Wg<P, TWO>;
     constexpr int Np = B::Np, Nfp = B::Nfp, NT = B::NT, KSV = B::KSV, VT = B::VT, GS = B::GS;
     constexpr int NL = Np - 8 * (NT - 1);                                          // nodes of the mixed tile
 #ifndef DGTD_WG_PF
 #define DGTD_WG_PF 3
 #endif
-#ifndef DGTD_WGX_PF
-#define DGTD_WGX_PF 3
+#ifndef DGTD_WG2_PF
+#define DGTD_WG2_PF 3
 #endif
-    constexpr int PF = P >= 4 ? 1 : DX ? DGTD_WGX_PF : DGTD_WG_PF;                 // neighbour-record prefetch distance (face steps)
-    constexpr bool NEED_X = MODE == MODE_STAGE1 || MODE == MODE_STAGE23;           // stage 1: x == y_in, fetched again (L2 hit)
-    constexpr bool NEED_Z = MODE == MODE_STAGE23 || MODE == MODE_STAGE4;
-    constexpr bool LOAD_X = NEED_X && !DX, LOAD_Z = NEED_Z && !DX;                 // staged through shared memory by bulk-TMA
+    constexpr int PF = P >= 4 ? 1 : TWO ? DGTD_WG2_PF : DGTD_WG_PF;                // neighbour-record prefetch distance (face steps)
+    constexpr bool NEED_X = MODE == MODE_STAGE1 || MODE == MODE_STAGE23;
+    constexpr bool LOAD_Z = MODE == MODE_STAGE23 || MODE == MODE_STAGE4;
+    // x by bulk load: always in the 3-buffer kernel (stage 1: x == y_in, fetched again, an L2 hit); with two buffers stage 1
+    // finds x in buffer A, which still holds y_in
+    constexpr bool LOAD_X = NEED_X && !(TWO && MODE == MODE_STAGE1);
     constexpr bool STORE_X = MODE != MODE_STAGE4, STORE_Z = MODE != MODE_MULT;      // stage 4 forms the new x in the z buffer
+    // two buffers: buffer A is busy (x / y_out) through the epilogue unless the stage has no x at all
+    constexpr bool Y_AFTER_STORE = TWO && MODE != MODE_STAGE4;
     extern __shared__ __align__(128) unsigned char smem_wg[];
     double *sm = reinterpret_cast<double *>(smem_wg);
     const double *sFragV = sm, *sFragL = sm + B::NFV * 32;
     const uint4 *sTab = reinterpret_cast<const uint4 *>(smem_wg + B::bTab);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, e = lane >> 2, j = lane & 3;
-    double *wY = sm + B::oWarp + warp * B::WDBL, *wX = wY + GS, *wZ = wX + GS, *wGeo = wY + B::NBUF * GS;   // DX: no wX / wZ
+    double *wY = sm + B::oWarp + warp * B::WDBL, *wX = TWO ? wY : wY + GS, *wZ = wX + GS, *wGeo = wY + B::NBUF * GS;   // TWO: x / y_out share buffer A with y_in
     const int2 *wDesc = reinterpret_cast<const int2 *>(wGeo + B::WGEO);
-    uint64_t *barY = reinterpret_cast<uint64_t *>(smem_wg + B::bBar) + 2 * warp, *barXZ = barY + 1;
+    uint64_t *barY = reinterpret_cast<uint64_t *>(smem_wg + B::bBar) + 3 * warp, *barX = barY + 1, *barZ = barY + 2;
 
-    uint64_t *barF = reinterpret_cast<uint64_t *>(smem_wg + B::bBar) + 2 * B::NW;   // operator fragments: one bulk copy per CTA
+    uint64_t *barF = reinterpret_cast<uint64_t *>(smem_wg + B::bBar) + 3 * B::NW;   // operator fragments: one bulk copy per CTA
     {
         uint4 *dst = reinterpret_cast<uint4 *>(smem_wg + B::bTab);
         const uint4 *src = reinterpret_cast<const uint4 *>(A.tab);
         for (int i = tid; i < min(A.ntab, B::TABROWS); i += B::T) dst[i] = src[i];
     }
     if (tid == 0) mbar_init(barF, 1);
-    if (lane == 0) { mbar_init(barY, 1); mbar_init(barXZ, 1); }
+    if (lane == 0) { mbar_init(barY, 1); mbar_init(barX, 1); mbar_init(barZ, 1); }
     if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
     __syncthreads();
 
     const int gstride = gridDim.x * B::NW;
-    int idx = blockIdx.x * B::NW + warp;                 // position in the processing order
-    const bool has_work = idx < A.ngroups;
-    int g = has_work && A.order ? A.order[idx] : idx;
-    unsigned peers_ready = A.pp.wait_epoch == 0 ? 0xffffffffu : 0u;
+    int g = blockIdx.x * B::NW + warp;
+    const bool has_work = g < A.ngroups;
+    bool halo_ready = A.pp.wait_epoch == 0;
     const uint4 ownrow = sTab[j];
     const bool inject = A.pw_on && (A.gate == nullptr || *A.gate >= 1e-16);
 
@@ -284,23 +241,29 @@ __global__ void __launch_bounds__(Wg<P, DX>::T, 1) stage_wg_kernel(const WgArgs 
         bulk_load(wGeo + B::WGEO, A.desc + (size_t)gg * B::WDESC, B::WDESC * 4, barY);
 #endif
     };
-    auto issue_xz = [&](int gg) {
-        mbar_expect_tx(barXZ, (uint32_t)(GS * 8) * ((LOAD_X ? 1 : 0) + (LOAD_Z ? 1 : 0)));
+    auto issue_x = [&](int gg) {
+        mbar_expect_tx(barX, (uint32_t)(GS * 8));
 #ifdef DGTD_L2_HINTS
-        if (LOAD_X) bulk_load_hint(wX, (MODE == MODE_STAGE1 ? A.yin : A.x) + (size_t)gg * GS, GS * 8, barXZ, polOnce);
-        if (LOAD_Z) bulk_load_hint(wZ, A.z + (size_t)gg * GS, GS * 8, barXZ, polOnce);
+        bulk_load_hint(wX, (MODE == MODE_STAGE1 ? A.yin : A.x) + (size_t)gg * GS, GS * 8, barX, polOnce);
 #else
-        if (LOAD_X) bulk_load(wX, (MODE == MODE_STAGE1 ? A.yin : A.x) + (size_t)gg * GS, GS * 8, barXZ);
-        if (LOAD_Z) bulk_load(wZ, A.z + (size_t)gg * GS, GS * 8, barXZ);
+        bulk_load(wX, (MODE == MODE_STAGE1 ? A.yin : A.x) + (size_t)gg * GS, GS * 8, barX);
+#endif
+    };
+    auto issue_z = [&](int gg) {
+        mbar_expect_tx(barZ, (uint32_t)(GS * 8));
+#ifdef DGTD_L2_HINTS
+        bulk_load_hint(wZ, A.z + (size_t)gg * GS, GS * 8, barZ, polOnce);
+#else
+        bulk_load(wZ, A.z + (size_t)gg * GS, GS * 8, barZ);
 #endif
     };
     if (tid == 0) { mbar_expect_tx(barF, (uint32_t)(B::NFR * 32 * 8)); bulk_load(sm, A.bfrag, B::NFR * 32 * 8, barF); }
-    if (lane == 0 && has_work) { issue_y(g); if (LOAD_X || LOAD_Z) issue_xz(g); }
+    if (lane == 0 && has_work) { issue_y(g); if (LOAD_X && !TWO) issue_x(g); if (LOAD_Z) issue_z(g); }
     mbar_wait(barF, 0);
 
-    for (int it = 0; idx < A.ngroups; idx += gstride, it++) {
+    for (int it = 0; g < A.ngroups; g += gstride, it++) {
         const uint32_t par = it & 1;
-        const int gnext = idx + gstride < A.ngroups ? (A.order ? A.order[idx + gstride] : idx + gstride) : -1;
+        const int gnext = g + gstride < A.ngroups ? g + gstride : -1;
         const double *ge = wGeo + e * WG_GEO;
         const double *yrec = wY + e * Np * 6;
         mbar_wait(barY, par);
@@ -334,8 +297,7 @@ __global__ void __launch_bounds__(Wg<P, DX>::T, 1) stage_wg_kernel(const WgArgs 
             nb_smem = false;
             nbase = A.halo + (size_t)(-2 - info.x) * Nfp * 6;
         }
-        const int mypeer = info.x < -1 ? (code >> FI_TAB_SHIFT) & FI_TAB_MASK : -1;      // partition face: peer index (WgPlan::desc)
-        if (peers_ready != 0xffffffffu) peers_ready = p2p_wait_peers(A.pp, mypeer, peers_ready);
+        if (!halo_ready && __any_sync(0xffffffffu, info.x < -1)) { p2p_wait(A.pp, lane); halo_ready = true; }
         double uQ[PF + 1][6];
 #pragma unroll
         for (int q = 0; q < PF; q++) load_rec_split(nbase + tab_byte(nrow, q) * 6, nb_smem, uQ[q]);
@@ -376,8 +338,13 @@ __global__ void __launch_bounds__(Wg<P, DX>::T, 1) stage_wg_kernel(const WgArgs 
                 }
             }
         }
-        // x / z of this group: the previous group's stores have long drained the buffers
-        if ((LOAD_X || LOAD_Z) && it > 0 && lane == 0) { bulk_wait_read(); issue_xz(g); }
+        // x / z of this group: the previous group's stores have long drained the buffers (two buffers: z came with y_in at the
+        // end of the previous group unless this is stage 4, x follows the flux)
+        if (it > 0 && lane == 0 && ((LOAD_X && !TWO) || (LOAD_Z && !Y_AFTER_STORE))) {
+            bulk_wait_read();
+            if (LOAD_X && !TWO) issue_x(g);
+            if (LOAD_Z) issue_z(g);
+        }
 
         // ---------------- face flux of (element e, face j) -> LIFT --------------------------------------------------------
         {
@@ -456,32 +423,24 @@ __global__ void __launch_bounds__(Wg<P, DX>::T, 1) stage_wg_kernel(const WgArgs 
         for (int i = 0; i < 9; i++) jm[i] = ge[i];
         const double de = ge[23], dm = ge[24], se = ge[25];          // det/eps, det/mu, sigma/eps  (jm = J / det)
         const double ae = A.a * de, am = A.a * dm, be = A.b * de, bm = A.b * dm;
-        const bool keep_y = A.has_sigma != 0;        // the conductivity term reads E of y_in in the epilogue
+        const bool keep_y = !TWO && A.has_sigma != 0;   // the conductivity term reads E of y_in in the epilogue (3-buffer kernel only)
         if (!keep_y) {
-            __syncwarp();
-            if (lane == 0 && gnext >= 0) issue_y(gnext);
+            __syncwarp();                               // every lane has read y_in for the last time
+            if (lane == 0) {
+                if (TWO && LOAD_X) issue_x(g);          // buffer A: y_in -> x
+                if (!Y_AFTER_STORE && gnext >= 0) issue_y(gnext);
+            }
         }
-        if (LOAD_X || LOAD_Z) mbar_wait(barXZ, par);
+        if (LOAD_X) mbar_wait(barX, par);
+        if (LOAD_Z) mbar_wait(barZ, par);
         // node slots of lane (e, j): nodes 8 nt + j and 8 nt + j + 4 of the full tiles, then node 8 (NT-1) + j of the mixed one
         constexpr int NS = 2 * (NT - 1) + 1;
-        const double *gX = DX ? (MODE == MODE_STAGE1 ? A.yin : A.x) + (size_t)g * GS + e * Np * 6 : nullptr;    // my element's records
-        const double *gZ = DX && NEED_Z ? A.z + (size_t)g * GS + e * Np * 6 : nullptr;
-        double *gO = DX ? A.yout + (size_t)g * GS + e * Np * 6 : nullptr, *gZo = DX ? A.z + (size_t)g * GS + e * Np * 6 : nullptr;
-        double xq[2][6], zq[2][6];                           // DX: x / z records of the next slot are in flight while this one is updated
         auto slot_node = [&](int sl) { return sl < NS - 1 ? 8 * (sl >> 1) + j + 4 * (sl & 1) : 8 * (NT - 1) + j; };
         auto slot_valid = [&](int sl) { return sl < NS - 1 || NL == 4 || j < NL; };
-        if (DX && (NEED_X || NEED_Z)) {
-            if (NEED_X) load_rec_global(gX + slot_node(0) * 6, xq[0]);
-            if (NEED_Z) load_rec_global(gZ + slot_node(0) * 6, zq[0]);
-        }
 #pragma unroll
         for (int sl = 0; sl < NS; sl++) {
             const int nt = sl < NS - 1 ? sl >> 1 : NT - 1, h = sl < NS - 1 ? sl & 1 : 0;
             const int node = slot_node(sl);
-            if (DX && (NEED_X || NEED_Z) && sl + 1 < NS && slot_valid(sl + 1)) {
-                if (NEED_X) load_rec_global(gX + slot_node(sl + 1) * 6, xq[(sl + 1) & 1]);
-                if (NEED_Z) load_rec_global(gZ + slot_node(sl + 1) * 6, zq[(sl + 1) & 1]);
-            }
             if (!slot_valid(sl)) continue;
             double kr[6];
             if (nt < NT - 1) {
@@ -511,13 +470,8 @@ __global__ void __launch_bounds__(Wg<P, DX>::T, 1) stage_wg_kernel(const WgArgs 
                 for (int c = 0; c < 6; c++) { ca[c] = A.a; cb[c] = A.b; }
             }
             double xv[6], zv[6], o[6], zn[6];
-            if (DX) {
-#pragma unroll
-                for (int c = 0; c < 6; c++) { xv[c] = xq[sl & 1][c]; zv[c] = zq[sl & 1][c]; }
-            } else {
-                if (LOAD_X) load_rec(wX + off, xv);
-                if (LOAD_Z) load_rec(wZ + off, zv);
-            }
+            if (NEED_X) load_rec(wX + off, xv);
+            if (LOAD_Z) load_rec(wZ + off, zv);
 #pragma unroll
             for (int c = 0; c < 6; c++) {
                 if (MODE == MODE_MULT) o[c] = k[c];
@@ -525,48 +479,41 @@ __global__ void __launch_bounds__(Wg<P, DX>::T, 1) stage_wg_kernel(const WgArgs 
                 else if (MODE == MODE_STAGE23) { o[c] = fma(ca[c], k[c], xv[c]); zn[c] = fma(cb[c], k[c], zv[c]); }
                 else zn[c] = fma(cb[c], k[c], zv[c]);          // stage 4: new x, formed in the z buffer
             }
-            if (DX) {
-                if (STORE_X) store_rec_global(gO + node * 6, o);
-                if (MODE == MODE_STAGE4) store_rec_global(gO + node * 6, zn);
-                else if (STORE_Z) store_rec_global(gZo + node * 6, zn);
-            } else {
-                if (STORE_X) store_rec(wX + off, o);
-                if (STORE_Z) store_rec(wZ + off, zn);
-            }
+            if (STORE_X) store_rec(wX + off, o);
+            if (STORE_Z) store_rec(wZ + off, zn);
         }
-        if (!DX) fence_async_smem();
+        fence_async_smem();
         __syncwarp();
-        if (MODE != MODE_MULT && A.pp.signal_epoch != 0 && __any_sync(0xffffffffu, info.x < -1)) {
-            if (info.x < -1) {                               // my traces of the new stage vector -> the peer's halo
-                const int2 hp = A.pp.hpush[-2 - info.x];
-                const uint4 prow = sTab[hp.x >> 8];
-                double *dst = A.pp.peer_out[hp.x & 0xff] + (size_t)hp.y * Nfp * 6;
-                const double *src = DX ? gO : (MODE == MODE_STAGE4 ? wZ : wX) + e * Np * 6;   // DX: what this warp just stored (L2)
+        if (MODE != MODE_MULT && A.pp.signal_epoch != 0 && info.x < -1) {   // my traces of the new stage vector -> the peer's halo
+            const int2 hp = A.pp.hpush[-2 - info.x];
+            const uint4 prow = sTab[hp.x >> 8];
+            double *dst = A.pp.peer_out[hp.x & 0xff] + (size_t)hp.y * Nfp * 6;
+            const double *src = (MODE == MODE_STAGE4 ? wZ : wX) + e * Np * 6;
 #pragma unroll
-                for (int m = 0; m < Nfp; m++) {
-                    double r[6];
-                    if (DX) load_rec_global_cg(src + tab_byte(prow, m) * 6, r);
-                    else load_rec(src + tab_byte(prow, m) * 6, r);
-                    store_rec(dst + m * 6, r);
-                }
+            for (int m = 0; m < Nfp; m++) {
+                double r[6];
+                load_rec(src + tab_byte(prow, m) * 6, r);
+                store_rec(dst + m * 6, r);
             }
-            p2p_arrive(A.pp, mypeer, lane);
         }
         if (lane == 0) {
-            if (!DX) {
-                const size_t goff = (size_t)g * GS;
-                if (STORE_X) bulk_store(A.yout + goff, wX, GS * 8);
-                if (MODE == MODE_STAGE4) bulk_store(A.yout + goff, wZ, GS * 8);
-                else if (STORE_Z) bulk_store(A.z + goff, wZ, GS * 8);
-                bulk_commit();
+            const size_t goff = (size_t)g * GS;
+            if (STORE_X) bulk_store(A.yout + goff, wX, GS * 8);
+            if (MODE == MODE_STAGE4) bulk_store(A.yout + goff, wZ, GS * 8);
+            else if (STORE_Z) bulk_store(A.z + goff, wZ, GS * 8);
+            bulk_commit();
+            if (Y_AFTER_STORE) {                        // two buffers: y_in (and z) of the next group once the stores have left A (and B)
+                bulk_wait_read();
+                if (gnext >= 0) { issue_y(gnext); if (LOAD_Z) issue_z(gnext); }
+            } else {
+                if (keep_y && gnext >= 0) issue_y(gnext);
+                if (!((LOAD_X && !TWO) || LOAD_Z)) bulk_wait_read();     // the next epilogue writes these buffers again
             }
-            if (keep_y && gnext >= 0) issue_y(gnext);
-            if (!DX && !(LOAD_X || LOAD_Z)) bulk_wait_read();     // the next epilogue writes these buffers again
         }
         __syncwarp();
-        g = gnext;
     }
-    if (!DX && lane == 0) bulk_wait_all();
+    if (lane == 0) bulk_wait_all();
+    if (MODE != MODE_MULT && A.pp.signal_epoch != 0) p2p_signal(A.pp);
 }
 
 // Stand-alone producer of an exchange (the state came from the host, or Mult was called on a foreign vector): the traces of

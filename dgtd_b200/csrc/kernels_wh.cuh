@@ -35,7 +35,7 @@ template <int P> struct Wh {
     static constexpr int NFV = KSV * VT, NFL = Nfp * NT, NFR = NFV + NFL;
     static constexpr int WGEO = WH_E * WG_GEO, WDESC = WH_E * 4 * 2;
     static constexpr int WDBL = 3 * GS + WGEO + WDESC / 2;
-    static constexpr int TABROWS = 136;
+    static constexpr int TABROWS = WG_TABROWS;
     static constexpr int oWarp = NFR * 32;
     static constexpr size_t bTab = (size_t)(oWarp + NW * WDBL) * 8;
     static constexpr size_t bBar = bTab + (size_t)TABROWS * 16;
@@ -83,10 +83,8 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
     __syncthreads();
 
     const int gstride = gridDim.x * B::NW, ngroups = A.ngroups * (BLK_E / WH_E);   // WgArgs counts groups of 8
-    int idx = blockIdx.x * B::NW + warp;                 // position in the processing order (units of 4 elements)
-    auto unit_at = [&](int i) { return A.order ? A.order[i >> 1] * 2 + (i & 1) : i; };      // WgPlan::order lists groups of 8
-    int g = idx < ngroups ? unit_at(idx) : idx;
-    unsigned peers_ready = A.pp.wait_epoch == 0 ? 0xffffffffu : 0u;
+    int g = blockIdx.x * B::NW + warp;
+    bool halo_ready = A.pp.wait_epoch == 0;
     const uint4 ownrow = sTab[j];
     const bool inject = A.pw_on && (A.gate == nullptr || *A.gate >= 1e-16);
     const double sgn = h ? -1.0 : 1.0;                   // u~_E = -(J/det)^T E feeds the H rows, u~_H = +(J/det)^T H the E rows
@@ -103,12 +101,12 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
         if (LOAD_Z) bulk_load(wZ, A.z + (size_t)gg * GS, GS * 8, barXZ);
     };
     if (tid == 0) { mbar_expect_tx(barF, (uint32_t)(B::NFR * 32 * 8)); bulk_load(sm, A.bfrag, B::NFR * 32 * 8, barF); }
-    if (leader && idx < ngroups) { issue_y(g); if (LOAD_X || LOAD_Z) issue_xz(g); }
+    if (leader && g < ngroups) { issue_y(g); if (LOAD_X || LOAD_Z) issue_xz(g); }
     mbar_wait(barF, 0);
 
-    for (int it = 0; idx < ngroups; idx += gstride, it++) {
+    for (int it = 0; g < ngroups; g += gstride, it++) {
         const uint32_t par = it & 1;
-        const int gnext = idx + gstride < ngroups ? unit_at(idx + gstride) : -1;
+        const int gnext = g + gstride < ngroups ? g + gstride : -1;
         const double *ge = wGeo + e * WG_GEO;
         const double *yrec = wY + e * Np * 6;
         mbar_wait(barY, par);
@@ -140,8 +138,7 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
             nb_smem = false;
             nbase = A.halo + (size_t)(-2 - info.x) * Nfp * 6;
         }
-        const int mypeer = info.x < -1 ? (code >> FI_TAB_SHIFT) & FI_TAB_MASK : -1;      // partition face: peer index (WgPlan::desc)
-        if (peers_ready != 0xffffffffu) peers_ready = p2p_wait_peers(A.pp, mypeer, peers_ready);
+        if (!halo_ready && __any_sync(0xffffffffu, info.x < -1)) { p2p_wait(A.pp, lane); halo_ready = true; }
         double uQ[PF + 1][6];
 #pragma unroll
         for (int q = 0; q < PF; q++) load_rec_split(nbase + tab_byte(nrow, q) * 6, nb_smem, uQ[q]);
@@ -297,20 +294,17 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
             }
         fence_async_smem();
         __syncwarp();                                       // complete records in wX / wZ
-        if (MODE != MODE_MULT && A.pp.signal_epoch != 0 && __any_sync(0xffffffffu, info.x < -1)) {
-            if (h == 0 && info.x < -1) {                     // the E-row lane of (element, face) ships the whole records
-                const int2 hp = A.pp.hpush[-2 - info.x];
-                const uint4 prow = sTab[hp.x >> 8];
-                double *dst = A.pp.peer_out[hp.x & 0xff] + (size_t)hp.y * Nfp * 6;
-                const double *src = (MODE == MODE_STAGE4 ? wZ : wX) + e * Np * 6;
+        if (MODE != MODE_MULT && A.pp.signal_epoch != 0 && h == 0 && info.x < -1) {   // the E-row lane of (element, face) ships the whole records
+            const int2 hp = A.pp.hpush[-2 - info.x];
+            const uint4 prow = sTab[hp.x >> 8];
+            double *dst = A.pp.peer_out[hp.x & 0xff] + (size_t)hp.y * Nfp * 6;
+            const double *src = (MODE == MODE_STAGE4 ? wZ : wX) + e * Np * 6;
 #pragma unroll
-                for (int m = 0; m < Nfp; m++) {
-                    double r[6];
-                    load_rec(src + tab_byte(prow, m) * 6, r);
-                    store_rec(dst + m * 6, r);
-                }
+            for (int m = 0; m < Nfp; m++) {
+                double r[6];
+                load_rec(src + tab_byte(prow, m) * 6, r);
+                store_rec(dst + m * 6, r);
             }
-            p2p_arrive(A.pp, h == 0 ? mypeer : -1, lane);
         }
         if (lane == 0) {
             const size_t goff = (size_t)g * GS;
@@ -322,9 +316,9 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
             if (!(LOAD_X || LOAD_Z)) bulk_wait_read();
         }
         __syncwarp();
-        g = gnext;
     }
     if (leader) bulk_wait_all();
+    if (MODE != MODE_MULT && A.pp.signal_epoch != 0) p2p_signal(A.pp);
 }
 
 }  // namespace dgtd

@@ -132,9 +132,6 @@ WgPlan build_wg_plan(const HostOp &H)
     };
 
     // ---- face descriptors ---------------------------------------------------------------------------------------------------
-    std::vector<int> peer_of_slot((size_t)H.n_halo_faces, 0);
-    for (size_t pi = 0; pi < H.peers.size(); pi++)
-        for (int s = H.peers[pi].recv_off; s < H.peers[pi].recv_off + H.peers[pi].nfaces; s++) peer_of_slot[(size_t)s] = (int)pi;
     W.desc.assign((size_t)W.NEpad * 8, 0);
     for (int e = 0; e < W.NEpad; e++)
         for (int f = 0; f < 4; f++) {
@@ -143,9 +140,7 @@ WgPlan build_wg_plan(const HostOp &H)
             const int nb = H.finfo[((size_t)e * 4 + f) * 2];
             int code = H.finfo[((size_t)e * 4 + f) * 2 + 1];
             const int old = (code >> FI_TAB_SHIFT) & FI_TAB_MASK;
-            // interior face: row of the neighbour's node table; boundary: own row; partition face: the table is always row
-            // 4 + f (canonical order of the halo slot), so the field carries the PEER INDEX the consumer waits for
-            int row = nb >= 0 ? nbr_row(f, old) : nb == -1 ? f : peer_of_slot[-2 - nb];
+            int row = nb >= 0 ? nbr_row(f, old) : nb == -1 ? f : 4 + f;
             if (row > FI_TAB_MASK) throw Error(DGTD_ERR_UNSUPPORTED, "too many distinct face orientations");
             code = (code & ~(FI_TAB_MASK << FI_TAB_SHIFT)) | (row << FI_TAB_SHIFT);
             fo[0] = nb; fo[1] = code;
@@ -198,32 +193,6 @@ WgPlan build_wg_plan(const HostOp &H)
                 W.hpush[(size_t)s * 2 + 1] = pp.remote_off + (s - pp.send_off);
             }
         }
-    }
-    // ---- processing order and per-peer push counts of the fused halo exchange -------------------------------------------------
-    // Units (groups of 8 elements; the half-row kernel works on their halves) that own a partition face come FIRST in a
-    // launch: their traces reach the neighbours while the interior is still being computed, and the flag of a peer is
-    // raised by whichever warp stores the last of the `need` units that push to it (kernels_wg.cuh: p2p_arrive).
-    W.order.resize((size_t)W.ngroups);
-    W.need8.assign(H.peers.size(), 0); W.need4.assign(H.peers.size(), 0);
-    {
-        std::vector<char> front((size_t)W.ngroups, 0);
-        for (int u = 0; u < 2 * W.ngroups; u++) {            // u = unit of 4 elements
-            unsigned mask = 0;
-            for (int e = 4 * u; e < std::min(4 * u + 4, NE); e++)
-                for (int f = 0; f < 4; f++) { const int nb = W.desc[((size_t)e * 4 + f) * 2]; if (nb < -1) mask |= 1u << peer_of_slot[-2 - nb]; }
-            for (size_t pi = 0; pi < H.peers.size(); pi++) if (mask >> pi & 1) W.need4[pi]++;
-            if (mask) front[(size_t)(u >> 1)] = 1;
-        }
-        for (int g = 0; g < W.ngroups; g++) {
-            unsigned mask = 0;
-            for (int e = 8 * g; e < std::min(8 * g + 8, NE); e++)
-                for (int f = 0; f < 4; f++) { const int nb = W.desc[((size_t)e * 4 + f) * 2]; if (nb < -1) mask |= 1u << peer_of_slot[-2 - nb]; }
-            for (size_t pi = 0; pi < H.peers.size(); pi++) if (mask >> pi & 1) W.need8[pi]++;
-        }
-        int k = 0;
-        for (int g = 0; g < W.ngroups; g++) if (front[(size_t)g]) W.order[(size_t)k++] = g;
-        W.nfront = k;
-        for (int g = 0; g < W.ngroups; g++) if (!front[(size_t)g]) W.order[(size_t)k++] = g;
     }
     // ---- halo pack list ---------------------------------------------------------------------------------------------------
     W.send_off.resize(H.send_node.size());

@@ -186,8 +186,7 @@ int  dgtd_kernel_info(const dgtd_ctx *, char *buf, int cap);
  * Replaces the six blocking MPI neighbour exchanges of GlobalEvolution::Mult (GlobalEvolution.cpp:763-774).
  * dgtd_comm_init is collective: NCCL bootstrap, then (tetrahedra, order <= 4) every rank maps its neighbours' halo
  * buffers with CUDA IPC; from then on the stage kernel itself stores the traces of its partition faces into the
- * neighbour's buffer (partition-face groups first in a launch, a neighbour's flag raised as soon as the last group touching
- * it has stored) and only the lanes owning such a face wait for that neighbour's epoch flag (no pack kernel, no
+ * neighbour's buffer and only the warps owning such a face wait for the neighbour's epoch flag (no pack kernel, no
  * collective on the path).  If IPC is unavailable on any rank, all ranks use ncclSend/ncclRecv instead.
  * dgtd_destroy of a multi-rank context is collective too (neighbours must stop storing before a buffer is freed).
  * Like the reference's MPI calls, every entry point that evaluates the operator or replaces the state (dgtd_mult,
@@ -204,8 +203,7 @@ int  dgtd_halo_bytes(const dgtd_ctx *, long long *bytes);
 
 /* Host-only diagnostic (no CUDA, no compute): copies one of the flat tables a rank would upload — "dims", "D", "lift",
  * "nodes", "fnodes", "geo", "finfo", "ftab", "elem_gid", "tfsf_xyz", "gate_xyz", "tfsf_side", "send_node", "peers", "peers5",
- * "node_coords", the plan of the warp-per-group kernel "wg_dims", "wg_bfrag", "wg_geo", "wg_forder", "wg_hpush", "wg_tab", "wg_desc", "wg_send_off", "wg_dev2ref", "wg_order",
- * "wg_need" (per peer: groups of 8 and of 4 elements pushing to it, then the number of front groups)
+ * "node_coords", the plan of the warp-per-group kernel "wg_dims", "wg_bfrag", "wg_geo", "wg_forder", "wg_hpush", "wg_tab", "wg_desc", "wg_send_off", "wg_dev2ref"
  * — so that tests can check the setup against the oracle without a GPU.                            */
 int  dgtd_setup_query(const dgtd_mesh *, const dgtd_options *, const char *name, void *buf, long long cap_bytes, long long *size_bytes);
 

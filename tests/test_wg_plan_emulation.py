@@ -18,8 +18,7 @@ def _plan(mesh, kw, **extra):
                 bfrag=q("wg_bfrag", np.float64).reshape(-1, 32), geo=q("wg_geo", np.float64).reshape(NEpad, GEO),
                 desc=q("wg_desc", np.int32).reshape(NEpad, 4, 2), tab=q("wg_tab", np.uint8).reshape(-1, 16),
                 d2r=q("wg_dev2ref", np.int32), gid=q("elem_gid", np.int32), dims=q("dims", np.int32),
-                hpush=q("wg_hpush", np.int32).reshape(-1, 2), peers=q("peers5", np.int32).reshape(-1, 5),
-                order=q("wg_order", np.int32), need=q("wg_need", np.int32), ngroups=ngroups)
+                hpush=q("wg_hpush", np.int32).reshape(-1, 2), peers=q("peers5", np.int32).reshape(-1, 5))
 
 
 def _frag_matrix(f):
@@ -190,21 +189,6 @@ def test_partitioned_plan_replay_with_pushed_traces(name, world, method):
     out = np.zeros(6 * O.N)
     owned = np.zeros(O.N, int)
     for r, P in enumerate(plans):
-        # fused-exchange tables: a partition face names its peer in the descriptor, the groups owning such faces come first in
-        # the processing order, and need[peer] counts the groups (of 8 / of 4 elements) that store traces to that peer
-        NE, npeers, ng = P["dims"][5], len(P["peers"]), P["ngroups"]
-        d = P["desc"]
-        for e in range(NE):
-            for f in range(4):
-                if d[e, f, 0] < -1:
-                    assert (d[e, f, 1] >> 4) & 0xff == P["hpush"][-2 - d[e, f, 0], 0] & 0xff
-        has = [sorted({int((d[e, f, 1] >> 4) & 0xff) for e in range(8 * g_, min(8 * g_ + 8, NE)) for f in range(4) if d[e, f, 0] < -1}) for g_ in range(ng)]
-        has4 = [sorted({int((d[e, f, 1] >> 4) & 0xff) for e in range(4 * u, min(4 * u + 4, NE)) for f in range(4) if d[e, f, 0] < -1}) for u in range(2 * ng)]
-        nfront = int(P["need"][-1])
-        assert sorted(P["order"].tolist()) == list(range(ng))
-        assert all(has[g_] for g_ in P["order"][:nfront]) and not any(has[g_] for g_ in P["order"][nfront:])
-        assert P["need"][:npeers].tolist() == [sum(p in h for h in has) for p in range(npeers)]
-        assert P["need"][npeers:2 * npeers].tolist() == [sum(p in h for h in has4) for p in range(npeers)]
         n_halo = sum(1 for e in range(P["dims"][5]) for f in range(4) if P["desc"][e, f, 0] < -1)
         assert sorted(halos[r]) == list(range(n_halo)), "every halo slot of a rank is written exactly by its neighbours"
         k = replay_mult(P, x, pb.alpha, halos[r]).reshape(6, -1)
