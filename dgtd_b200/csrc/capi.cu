@@ -118,10 +118,10 @@ static KernelSet select_kernels(int dim, int p)
 // the warp-per-group kernel: tetrahedra of order 1..4, element-major "aos" layout, one warp per group of 8 elements
 typedef void (*WgFn)(const WgArgs);
 struct WgSet { WgFn fn[4]; int threads; size_t smem; };
-template <int P, bool TF, bool TWO = false> static WgSet wgset()
+template <int P, bool TF> static WgSet wgset()
 {
-    using B = Wg<P, TWO>;
-    return {{stage_wg_kernel<P, 0, TF, TWO>, stage_wg_kernel<P, 1, TF, TWO>, stage_wg_kernel<P, 2, TF, TWO>, stage_wg_kernel<P, 3, TF, TWO>}, B::T, B::smem_bytes};
+    using B = Wg<P>;
+    return {{stage_wg_kernel<P, 0, TF>, stage_wg_kernel<P, 1, TF>, stage_wg_kernel<P, 2, TF>, stage_wg_kernel<P, 3, TF>}, B::T, B::smem_bytes};
 }
 // tf = the context injects a TF/SF plane wave
 static bool select_wg(int dim, int p, bool tf, WgSet &ws)
@@ -133,18 +133,6 @@ static bool select_wg(int dim, int p, bool tf, WgSet &ws)
     }
     return false;
 }
-// the same kernel with two instead of three group buffers per warp (kernels_wg.cuh: TWO): 12 instead of 8 warps per SM at
-// order <= 3; not for contexts with conductivity
-static bool select_wg2(int dim, int p, bool tf, WgSet &ws)
-{
-    if (dim != 3) return false;
-    switch (p) {
-        case 1: ws = tf ? wgset<1, true, true>() : wgset<1, false, true>(); return true; case 2: ws = tf ? wgset<2, true, true>() : wgset<2, false, true>(); return true;
-        case 3: ws = tf ? wgset<3, true, true>() : wgset<3, false, true>(); return true; case 4: ws = tf ? wgset<4, true, true>() : wgset<4, false, true>(); return true;
-    }
-    return false;
-}
-
 // the half-row kernel (kernels_wh.cuh): same plan and layout, one warp per group of FOUR elements, rows = (element, field)
 template <int P, bool TF> static WgSet whset()
 {
@@ -167,7 +155,6 @@ struct dgtd_ctx {
     HostOp H;
     WgPlan WP;
     bool has_sigma = false;
-    bool wg2 = false;                // ... with two group buffers per warp (12 warps per SM)
     bool wh = false;                 // ... or its half-row form (kernels_wh.cuh, groups of 4 elements); wg stays set: same plan and layout
     int wg_groups_per_cta = 0;
     bool wg = false;                 // aos layout + warp-per-group kernel (the state needs a layout conversion at the ABI)
@@ -611,11 +598,6 @@ int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
         c->WP = build_wg_plan(H);
         if (c->WP.ntab <= Wg<3>::TABROWS) c->wg = c->wh = true;
     }
-    if (!c->wg && ksel == "wg2" && !has_sigma && select_wg2(H.dim, H.p, has_tf, c->wgs) && c->wgs.smem <= (size_t)prop.sharedMemPerBlockOptin) {
-        c->WP = build_wg_plan(H);
-        c->wg_groups_per_cta = c->wgs.threads / 32;
-        if (c->WP.ntab <= Wg<3>::TABROWS) c->wg = c->wg2 = true;
-    }
     if (!c->wg && (ksel == "wg" || ksel == "wh" || ksel.empty()) && select_wg(H.dim, H.p, has_tf, c->wgs) && c->wgs.smem <= (size_t)prop.sharedMemPerBlockOptin) {
         c->WP = build_wg_plan(H);
         c->wg_groups_per_cta = c->wgs.threads / 32;
@@ -1026,9 +1008,8 @@ int dgtd_kernel_info(const dgtd_ctx *c, char *buf, int cap)
         std::snprintf(tmp, sizeof tmp, "stage_wh_kernel<P=%d,MODE> DMMA m8n8k4 transposed, warp per group of 4 elements (rows = element x field), aos layout, %d threads, %zu B smem, grid %d%s",
                       c->H.p, c->wgs.threads, c->wgs.smem, c->grid, c->nranks == 1 ? "" : c->p2p ? ", halo: fused peer-memory stores" : ", halo: NCCL send/recv");
     else if (c->wg)
-        std::snprintf(tmp, sizeof tmp, "stage_wg_kernel<P=%d,MODE%s> DMMA m8n8k4 transposed, warp per group of 8 elements, aos layout%s, %d threads, %zu B smem, grid %d%s",
-                      c->H.p, c->wg2 ? ",TWO" : "", c->wg2 ? ", 2 group buffers per warp" : "", c->wgs.threads, c->wgs.smem, c->grid,
-                      c->nranks == 1 ? "" : c->p2p ? ", halo: fused peer-memory stores" : ", halo: NCCL send/recv");
+        std::snprintf(tmp, sizeof tmp, "stage_wg_kernel<P=%d,MODE> DMMA m8n8k4 transposed, warp per group of 8 elements, aos layout, %d threads, %zu B smem, grid %d%s",
+                      c->H.p, c->wgs.threads, c->wgs.smem, c->grid, c->nranks == 1 ? "" : c->p2p ? ", halo: fused peer-memory stores" : ", halo: NCCL send/recv");
     else
         std::snprintf(tmp, sizeof tmp, "stage_kernel<DIM=%d,P=%d,MODE> generic, %d threads, %zu B smem, grid %d", c->H.dim, c->H.p, c->ks.threads, c->ks.smem, c->grid);
     std::snprintf(buf, (size_t)cap, "%s", tmp);

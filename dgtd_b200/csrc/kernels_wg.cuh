@@ -109,28 +109,22 @@ struct WgArgs {
     WgP2P pp;
 };
 
-// TWO: two group buffers per warp instead of three, so that 12 warps (3 per scheduler) instead of 8 fit on an SM at order
-// <= 3 — the FP64 pipe idles whenever every warp of a scheduler sits in a load wait or in the epilogue (ncu: pipe 73 % busy
-// with 2 warps per scheduler).  Buffer A holds y_in until the flux is done, then x (bulk load after the last read of y_in;
-// stage 1: x IS y_in, nothing to load) and finally y_out in place; buffer B holds z, loaded early, and z_new in place.  The
-// price: the next group's y_in can only be requested once the stores have left buffer A (stage 4 and the 3-buffer kernel
-// request it at the start of the epilogue), and the x load of stages 2-3 is exposed — latencies a third warp covers.
-// Not for contexts with conductivity (the epilogue then reads E of y_in, which buffer A no longer holds).
-template <int P, bool TWO = false> struct Wg {
+// Warps per SM: the three group buffers of a warp (y_in, x -> y_out, z -> z_new: 23 KB at order 3) and 222 registers put
+// 8 warps on an SM at order <= 3 and 4 at order 4.  Two ways to a third warp per scheduler were built and measured in
+// round 2 (both parity-green, both slower: profiles/r2_warp_count_experiments.txt): x / z through per-lane
+// global accesses instead of staging (12 warps, 91 G vs 120 G) and two buffers with x loaded over y_in after the flux
+// (12 warps at 168 registers, 99-105 G).
+template <int P> struct Wg {
     static constexpr int Np = (P + 1) * (P + 2) * (P + 3) / 6, Nfp = (P + 1) * (P + 2) / 2;
     static constexpr int NT = (Np + 7) / 8, KSV = (Np + 3) / 4, VT = (NT - 1) * 3 + 3;
 #ifndef DGTD_WG_NW
 #define DGTD_WG_NW 8
 #endif
-#ifndef DGTD_WG2_NW
-#define DGTD_WG2_NW 12
-#endif
-    static constexpr int NW = TWO ? (P <= 3 ? DGTD_WG2_NW : 6) : (P <= 3 ? DGTD_WG_NW : 4), T = 32 * NW;   // warps per CTA = groups in flight per SM
+    static constexpr int NW = P <= 3 ? DGTD_WG_NW : 4, T = 32 * NW;   // warps per CTA = groups in flight per SM
     static constexpr int GS = Np * BLK_E * 6;                    // doubles per group of one state vector
     static constexpr int NFV = KSV * VT, NFL = Nfp * NT, NFR = NFV + NFL;
     static constexpr int WGEO = BLK_E * WG_GEO, WDESC = BLK_E * 4 * 2;   // doubles / ints per group
-    static constexpr int NBUF = TWO ? 2 : 3;                     // group buffers per warp
-    static constexpr int WDBL = NBUF * GS + WGEO + WDESC / 2;    // doubles per warp: buffers, geometry, descriptors
+    static constexpr int WDBL = 3 * GS + WGEO + WDESC / 2;       // doubles per warp: Y, X, Z, geometry, descriptors
     static constexpr int TABROWS = WG_TABROWS;
     static constexpr int oWarp = NFR * 32;
     static constexpr size_t bTab = (size_t)(oWarp + NW * WDBL) * 8;
@@ -177,34 +171,26 @@ __device__ __forceinline__ void store_rec(double *p, const double *u)
 // Measured alternatives (profiles/): one-step prefetch issued inside the face loop with the flux in physical
 // components, 97.9 G vs 110 G; asm-volatile (pinned) prefetch loads, +-0; prefetch.global.L1 of the records, -9 %.
 // TF: the context has a TF/SF plane-wave source (the injection code sits in the face loop only then).
-template <int P, int MODE, bool TF, bool TWO>
-__global__ void __launch_bounds__(Wg<P, TWO>::T, 1) stage_wg_kernel(const WgArgs A)
+template <int P, int MODE, bool TF>
+__global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
 {
-    using B = Wg<P, TWO>;
+    using B = Wg<P>;
     constexpr int Np = B::Np, Nfp = B::Nfp, NT = B::NT, KSV = B::KSV, VT = B::VT, GS = B::GS;
     constexpr int NL = Np - 8 * (NT - 1);                                          // nodes of the mixed tile
 #ifndef DGTD_WG_PF
 #define DGTD_WG_PF 3
 #endif
-#ifndef DGTD_WG2_PF
-#define DGTD_WG2_PF 3
-#endif
-    constexpr int PF = P >= 4 ? 1 : TWO ? DGTD_WG2_PF : DGTD_WG_PF;                // neighbour-record prefetch distance (face steps)
-    constexpr bool NEED_X = MODE == MODE_STAGE1 || MODE == MODE_STAGE23;
+    constexpr int PF = P >= 4 ? 1 : DGTD_WG_PF;                                    // neighbour-record prefetch distance (face steps)
+    constexpr bool LOAD_X = MODE == MODE_STAGE1 || MODE == MODE_STAGE23;           // stage 1: x == y_in, fetched again (L2 hit)
     constexpr bool LOAD_Z = MODE == MODE_STAGE23 || MODE == MODE_STAGE4;
-    // x by bulk load: always in the 3-buffer kernel (stage 1: x == y_in, fetched again, an L2 hit); with two buffers stage 1
-    // finds x in buffer A, which still holds y_in
-    constexpr bool LOAD_X = NEED_X && !(TWO && MODE == MODE_STAGE1);
     constexpr bool STORE_X = MODE != MODE_STAGE4, STORE_Z = MODE != MODE_MULT;      // stage 4 forms the new x in the z buffer
-    // two buffers: buffer A is busy (x / y_out) through the epilogue unless the stage has no x at all
-    constexpr bool Y_AFTER_STORE = TWO && MODE != MODE_STAGE4;
     extern __shared__ __align__(128) unsigned char smem_wg[];
     double *sm = reinterpret_cast<double *>(smem_wg);
     const double *sFragV = sm, *sFragL = sm + B::NFV * 32;
     const uint4 *sTab = reinterpret_cast<const uint4 *>(smem_wg + B::bTab);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, e = lane >> 2, j = lane & 3;
-    double *wY = sm + B::oWarp + warp * B::WDBL, *wX = TWO ? wY : wY + GS, *wZ = wX + GS, *wGeo = wY + B::NBUF * GS;   // TWO: x / y_out share buffer A with y_in
+    double *wY = sm + B::oWarp + warp * B::WDBL, *wX = wY + GS, *wZ = wX + GS, *wGeo = wZ + GS;
     const int2 *wDesc = reinterpret_cast<const int2 *>(wGeo + B::WGEO);
     uint64_t *barY = reinterpret_cast<uint64_t *>(smem_wg + B::bBar) + 3 * warp, *barX = barY + 1, *barZ = barY + 2;
 
@@ -258,7 +244,7 @@ __global__ void __launch_bounds__(Wg<P, TWO>::T, 1) stage_wg_kernel(const WgArgs
 #endif
     };
     if (tid == 0) { mbar_expect_tx(barF, (uint32_t)(B::NFR * 32 * 8)); bulk_load(sm, A.bfrag, B::NFR * 32 * 8, barF); }
-    if (lane == 0 && has_work) { issue_y(g); if (LOAD_X && !TWO) issue_x(g); if (LOAD_Z) issue_z(g); }
+    if (lane == 0 && has_work) { issue_y(g); if (LOAD_X) issue_x(g); if (LOAD_Z) issue_z(g); }
     mbar_wait(barF, 0);
 
     for (int it = 0; g < A.ngroups; g += gstride, it++) {
@@ -338,11 +324,10 @@ __global__ void __launch_bounds__(Wg<P, TWO>::T, 1) stage_wg_kernel(const WgArgs
                 }
             }
         }
-        // x / z of this group: the previous group's stores have long drained the buffers (two buffers: z came with y_in at the
-        // end of the previous group unless this is stage 4, x follows the flux)
-        if (it > 0 && lane == 0 && ((LOAD_X && !TWO) || (LOAD_Z && !Y_AFTER_STORE))) {
+        // x / z of this group: the previous group's stores have long drained the buffers
+        if ((LOAD_X || LOAD_Z) && it > 0 && lane == 0) {
             bulk_wait_read();
-            if (LOAD_X && !TWO) issue_x(g);
+            if (LOAD_X) issue_x(g);
             if (LOAD_Z) issue_z(g);
         }
 
@@ -423,13 +408,10 @@ __global__ void __launch_bounds__(Wg<P, TWO>::T, 1) stage_wg_kernel(const WgArgs
         for (int i = 0; i < 9; i++) jm[i] = ge[i];
         const double de = ge[23], dm = ge[24], se = ge[25];          // det/eps, det/mu, sigma/eps  (jm = J / det)
         const double ae = A.a * de, am = A.a * dm, be = A.b * de, bm = A.b * dm;
-        const bool keep_y = !TWO && A.has_sigma != 0;   // the conductivity term reads E of y_in in the epilogue (3-buffer kernel only)
+        const bool keep_y = A.has_sigma != 0;        // the conductivity term reads E of y_in in the epilogue
         if (!keep_y) {
-            __syncwarp();                               // every lane has read y_in for the last time
-            if (lane == 0) {
-                if (TWO && LOAD_X) issue_x(g);          // buffer A: y_in -> x
-                if (!Y_AFTER_STORE && gnext >= 0) issue_y(gnext);
-            }
+            __syncwarp();                            // every lane has read y_in for the last time
+            if (lane == 0 && gnext >= 0) issue_y(gnext);
         }
         if (LOAD_X) mbar_wait(barX, par);
         if (LOAD_Z) mbar_wait(barZ, par);
@@ -470,7 +452,7 @@ __global__ void __launch_bounds__(Wg<P, TWO>::T, 1) stage_wg_kernel(const WgArgs
                 for (int c = 0; c < 6; c++) { ca[c] = A.a; cb[c] = A.b; }
             }
             double xv[6], zv[6], o[6], zn[6];
-            if (NEED_X) load_rec(wX + off, xv);
+            if (LOAD_X) load_rec(wX + off, xv);
             if (LOAD_Z) load_rec(wZ + off, zv);
 #pragma unroll
             for (int c = 0; c < 6; c++) {
@@ -502,13 +484,8 @@ __global__ void __launch_bounds__(Wg<P, TWO>::T, 1) stage_wg_kernel(const WgArgs
             if (MODE == MODE_STAGE4) bulk_store(A.yout + goff, wZ, GS * 8);
             else if (STORE_Z) bulk_store(A.z + goff, wZ, GS * 8);
             bulk_commit();
-            if (Y_AFTER_STORE) {                        // two buffers: y_in (and z) of the next group once the stores have left A (and B)
-                bulk_wait_read();
-                if (gnext >= 0) { issue_y(gnext); if (LOAD_Z) issue_z(gnext); }
-            } else {
-                if (keep_y && gnext >= 0) issue_y(gnext);
-                if (!((LOAD_X && !TWO) || LOAD_Z)) bulk_wait_read();     // the next epilogue writes these buffers again
-            }
+            if (keep_y && gnext >= 0) issue_y(gnext);
+            if (!(LOAD_X || LOAD_Z)) bulk_wait_read();            // the next epilogue writes these buffers again
         }
         __syncwarp();
     }

@@ -209,24 +209,47 @@ HostOp build_host_op(const Mesh &m, const Options &o)
     // ---- TF/SF sides (SubMesher.cpp:677-771) ---------------------------------------------------------------
     std::vector<int> side(NE, 0), faceTF((size_t)NE * nf, 0);
     if (!tfsfTags.empty() && o.pw.enabled) {
-        if (dim != 3) throw Error(DGTD_ERR_UNSUPPORTED, "TF/SF sources are supported on tetrahedral meshes only");
         std::set<int> counted; double ctr[3] = {0, 0, 0};
         for (int b = 0; b < m.nbe(); b++) if (tfsfTags.count(m.bdr_attr[b]))
             for (int c = 0; c < dim; c++) { int v = m.bdr[(size_t)b * dim + c]; if (counted.insert(v).second) for (int q = 0; q < 3; q++) ctr[q] += m.verts[3 * (size_t)v + q]; }
         if (!counted.empty()) for (int q = 0; q < 3; q++) ctr[q] /= (double)counted.size();
-        auto dist2 = [&](int e) {
-            double bc3[3] = {0, 0, 0};
+        auto bary = [&](int e, double *bc3) {
+            for (int q = 0; q < 3; q++) bc3[q] = 0;
             for (int k = 0; k < nf; k++) for (int q = 0; q < 3; q++) bc3[q] += m.verts[3 * (size_t)m.elems[(size_t)e * nf + k] + q];
-            double s = 0; for (int q = 0; q < 3; q++) { bc3[q] /= nf; s += (bc3[q] - ctr[q]) * (bc3[q] - ctr[q]); }
+            for (int q = 0; q < 3; q++) bc3[q] /= nf;
+        };
+        auto dist2 = [&](int e) {
+            double bc3[3]; bary(e, bc3);
+            double s = 0; for (int q = 0; q < 3; q++) s += (bc3[q] - ctr[q]) * (bc3[q] - ctr[q]);
             return s;
         };
+        int nTfsfBdr = 0;
+        for (int b = 0; b < m.nbe(); b++) nTfsfBdr += tfsfTags.count(m.bdr_attr[b]) ? 1 : 0;
+        if (dim == 1 && nTfsfBdr > 2) throw Error(DGTD_ERR_ARG, "only one or two TF/SF points can be declared on a 1-D mesh");   // SubMesher.cpp:563
         std::vector<std::pair<int, int>> tfFaces;
+        int seen = 0;
         for (int b = 0; b < m.nbe(); b++) {
             if (!tfsfTags.count(m.bdr_attr[b])) continue;
             // Elem1 = the face's first element in MFEM = lower element id
             const FaceKey &s0 = sorted[bdrElemFace[b]], &s1 = sorted[bdrElemFace[b] + 1];
             const FaceKey &a = s0.e < s1.e ? s0 : s1, &c = s0.e < s1.e ? s1 : s0;
-            bool e1tf = dist2(a.e) < dist2(c.e);
+            bool e1tf;
+            if (dim == 3) e1tf = dist2(a.e) < dist2(c.e);          // centroid rule (SubMesher.cpp:677-771)
+            else if (dim == 2) {
+                // orientation rule (SubMesher.cpp:568-660): cross(barycentre(Elem1) -> barycentre(Elem2), face tangent)_z >= 0
+                // makes Elem1 the scattered-field side; the face's vertices are Elem1's local edge (MFEM GenerateFaces)
+                static const int ev[3][2] = {{1, 2}, {2, 0}, {0, 1}};      // edge opposite vertex f, in the element's orientation
+                const int v0 = m.elems[(size_t)a.e * nf + ev[a.f][0]], v1 = m.elems[(size_t)a.e * nf + ev[a.f][1]];
+                double b1[3], b2[3]; bary(a.e, b1); bary(c.e, b2);
+                const double tx = m.verts[3 * (size_t)v1] - m.verts[3 * (size_t)v0], ty = m.verts[3 * (size_t)v1 + 1] - m.verts[3 * (size_t)v0 + 1];
+                const double ori = (b2[0] - b1[0]) * ty - (b2[1] - b1[1]) * tx;
+                e1tf = !(ori >= 0.0);
+            } else {
+                // one point: Elem1 scattered, Elem2 total; two points, in boundary-element order: the first like that, the
+                // second the other way round, so that the total field lies between them (SubMesher.cpp:476-547)
+                e1tf = seen == 1;
+            }
+            seen++;
             auto mark = [&](int e, bool tf) { if (!tf) side[e] = 2; else if (side[e] == 0) side[e] = 1; };
             mark(a.e, e1tf); mark(c.e, !e1tf);
             tfFaces.push_back({a.e, a.f}); tfFaces.push_back({c.e, c.f});

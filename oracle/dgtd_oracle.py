@@ -321,17 +321,27 @@ class HesthavenOracle:
         self.tfsf_face = np.zeros((NE, nf), np.int32)   # +1: this side is TF, -1: this side is SF
         tags = set(pb.tfsf_tags)
         if tags:
-            if dim != 3:
-                raise NotImplementedError("TF/SF side rule restated for 3-D only")
             vs = sorted({int(v) for b, a in zip(pb.bdr, pb.bdr_attr) if int(a) in tags for v in b})
             ctr = pb.verts[vs, :3].sum(axis=0) / len(vs)
             bary_e = pb.verts[pb.elems][:, :, :3].sum(axis=1) / (dim + 1)
             d2 = ((bary_e - ctr) ** 2).sum(axis=1)
+            seen = 0
+            if dim == 1 and sum(1 for a in pb.bdr_attr if int(a) in tags) > 2:
+                raise ValueError("only one or two TF/SF points can be declared on a 1-D mesh")     # SubMesher.cpp:563
             for b, a in zip(pb.bdr, pb.bdr_attr):      # boundary-element order, as the reference loops
                 if int(a) not in tags:
                     continue
-                (e1, f1), (e2, f2) = faces[tuple(sorted(int(v) for v in b))]
-                e1_tf = d2[e1] < d2[e2]
+                (e1, f1), (e2, f2) = sorted(faces[tuple(sorted(int(v) for v in b))])   # Elem1 = the lower element id (MFEM)
+                if dim == 3:                                   # centroid rule, SubMesher.cpp:677-771
+                    e1_tf = d2[e1] < d2[e2]
+                elif dim == 2:                                 # orientation rule, SubMesher.cpp:568-660, 239-250, 281-290
+                    ev = ((1, 2), (2, 0), (0, 1))[f1]          # Elem1's local edge opposite vertex f1, in its orientation
+                    t = pb.verts[pb.elems[e1, ev[1]], :2] - pb.verts[pb.elems[e1, ev[0]], :2]
+                    bb = bary_e[e2, :2] - bary_e[e1, :2]
+                    e1_tf = not (bb[0] * t[1] - bb[1] * t[0] >= 0.0)
+                else:                                          # SubMesher.cpp:476-547: SF|TF at the first point, TF|SF at the second
+                    e1_tf = seen == 1
+                seen += 1
                 for (e, f, tf) in ((e1, f1, e1_tf), (e2, f2, not e1_tf)):
                     self.tfsf_face[e, f] = 1 if tf else -1
                     if not tf:

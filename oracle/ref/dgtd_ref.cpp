@@ -564,7 +564,6 @@ static TFSFSource buildTFSFSource(Factory &F, const std::vector<double> &xyz)
    TFSFSource S; Mesh &m = *F.fes.GetMesh();
    S.elemSide.assign(m.GetNE(), 0);
    if (F.tfsfMarker.Size() == 0) { return S; }
-   if (m.Dimension() != 3) { MFEM_ABORT("oracle: TF/SF side classification is restated for 3-D meshes only"); }
    double ctr[3] = {0, 0, 0}; int nv = 0; std::set<int> counted; Array<int> verts;
    for (int be = 0; be < m.GetNBE(); be++)
    {
@@ -581,6 +580,7 @@ static TFSFSource buildTFSFSource(Factory &F, const std::vector<double> &xyz)
       for (int i = 0; i < v.Size(); i++) { const double *p = m.GetVertex(v[i]); for (int d = 0; d < 3; d++) { b[d] += p[d]; } }
       for (int d = 0; d < 3; d++) { b[d] /= v.Size(); }
    };
+   int seen1d = 0;
    for (int be = 0; be < m.GetNBE(); be++)
    {
       if (F.tfsfMarker[m.GetBdrAttribute(be) - 1] != 1) { continue; }
@@ -589,7 +589,19 @@ static TFSFSource buildTFSFSource(Factory &F, const std::vector<double> &xyz)
       double b1[3], b2[3]; bary(e1, b1); bary(e2, b2);
       double d1 = 0, d2 = 0;
       for (int d = 0; d < 3; d++) { d1 += (b1[d] - ctr[d]) * (b1[d] - ctr[d]); d2 += (b2[d] - ctr[d]) * (b2[d] - ctr[d]); }
-      bool e1tf = d1 < d2;
+      bool e1tf;
+      if (m.Dimension() == 3) { e1tf = d1 < d2; }                       // centroid rule, SubMesher.cpp:677-771
+      else if (m.Dimension() == 2)
+      {
+         // setIndividualTFSFAttributesForSubMeshing2D (:568-660): cross(Elem1 -> Elem2 barycentres, face tangent)_z >= 0 puts
+         // Elem1 on the scattered-field side; the tangent runs along m.GetFace(f)'s vertices (buildTangent2D, :239-250)
+         const int *fv = m.GetFace(f)->GetVertices();
+         const double *v0 = m.GetVertex(fv[0]), *v1 = m.GetVertex(fv[1]);
+         const double ori = (b2[0] - b1[0]) * (v1[1] - v0[1]) - (b2[1] - b1[1]) * (v1[0] - v0[0]);
+         e1tf = !(ori >= 0.0);
+      }
+      else { e1tf = seen1d == 1; }                                       // assignIndividualTFSFAtts{One,Two}Point(s)1D, :476-547
+      seen1d++;
       // SF marks override TF marks (sf_dof_set applied last, SourcesManager.cpp:173-187)
       auto mark = [&](int e, bool tf) { if (!tf) { S.elemSide[e] = 2; } else if (S.elemSide[e] == 0) { S.elemSide[e] = 1; } };
       mark(e1, e1tf); mark(e2, !e1tf);

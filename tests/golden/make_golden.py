@@ -197,6 +197,16 @@ def two_material_mesh(path):
 if __name__ == "__main__":
     if not os.path.exists(REF):
         sys.exit("build oracle/_ref first: make -C oracle/ref")
+    if len(sys.argv) > 1 and sys.argv[1] == "tfsf12":
+        # the reference's own 1-D and 2-D TF/SF cases (test/cases/CasesTest.cpp:230-454 `1D_TFSF`, ExtensiveCasesTest.cpp `2D_TFSF`):
+        # meshes and source parameters of testData/maxwellInputs/{1D_TFSF,2D_TFSF}/*.json, started when the pulse sits on the
+        # TF/SF points / line (auto delay of driver.cpp:576-589: the pulse centre reaches them at t = 5 sqrt(2) spread)
+        R = "/root/reference/testData/maxwellInputs"
+        run("tfsf1d_ref_p3", f"--mesh {R}/1D_TFSF/1D_TFSF.msh --order 3 --alpha 1.0 --bdr 1:pec,2:pec --tfsf 3,4 --pw 0.6:auto:0:0,1,0:1,0,0 --init random:21 --t0 4.0 --dt 0.01 --steps 40".split(),
+            {"bdr": {"1": "pec", "2": "pec"}, "tfsf": [3, 4]})
+        run("tfsf2d_ref_p3", f"--mesh {R}/2D_TFSF/2D_TFSF.msh --order 3 --alpha 1.0 --bdr 1:pec,3:pec,5:pec,7:pec,4:pmc,6:pmc --tfsf 2 --pw 0.4:auto:0:0,1,0:1,0,0 --init random:22 --t0 2.7 --dt 0.01 --steps 20".split(),
+            {"bdr": {"1": "pec", "3": "pec", "5": "pec", "7": "pec", "4": "pmc", "6": "pmc"}, "tfsf": [2]})
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "interior":
         interior_cases()
         sys.exit(0)

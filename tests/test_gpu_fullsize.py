@@ -1,4 +1,5 @@
-"""Size-independent properties of the CUDA path at BASELINE.json's full sizes (no oracle can run there in seconds):
+"""The CUDA path at BASELINE.json's full sizes: one direct comparison with the portable oracle at the bench size, and
+size-independent properties:
 linearity of Mult at the bench size, exact curl of polynomial fields, the fused RK4 step against four Mult calls,
 and the analytic PEC-cavity mode the reference's own solver tests use as behavioural pin
 (test/maxwell/solver/Solver3DTest.cpp:57-102: tets, order 3, PEC box, returns to the analytic state)."""
@@ -42,6 +43,25 @@ def test_mult_is_linear_at_the_bench_size(dg):
     assert rel_l2(kl, kx) < 1e-13
     assert np.isfinite(kl).all() and np.linalg.norm(kl) > 0
     assert "stage_wg_kernel" in ev.kernel_info()
+    ev.close()
+
+
+def test_bench_size_mult_and_rk4_step_match_the_oracle(dg):
+    """The bench workload itself (32^3 cubes x 6 tets, order 3, 23.6 M DOFs) against the portable oracle on the FULL vectors:
+    one Mult and one fused RK4 step (the numpy oracle needs ~15 s of setup and ~4 s per Mult at this size)."""
+    from oracle.dgtd_oracle import PEC, HesthavenOracle, Problem
+    mesh = dg.Mesh.cartesian3d(32)
+    v, e, ea, b, ba = mesh.arrays()
+    O = HesthavenOracle(Problem(v, e.astype(np.int64), ea, b.astype(np.int64), ba, ORDER, 1.0, {a: PEC for a in range(1, 7)}))
+    ev = dg.Evolution(mesh, order=ORDER, alpha=1.0, bdr={a: dg.BC_PEC for a in range(1, 7)})
+    assert 6 * ev.N == 23592960 == 6 * O.N
+    x = np.random.default_rng(5).standard_normal(6 * ev.N)
+    ev.SetTime(0.0)
+    assert rel_l2(ev.Mult(x), O.mult(0.0, x)) < 1e-12
+    dt = 0.05 / 32 / 9
+    ev.set_state(x)
+    ev.Step(0.0, dt)
+    assert rel_l2(ev.get_state(), O.rk4_step(x, 0.0, dt)) < 1e-12      # north_star: 1e-10 per step
     ev.close()
 
 
