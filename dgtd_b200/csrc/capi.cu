@@ -179,15 +179,14 @@ struct dgtd_ctx {
     DevPlaneWave pw{};
     int pw_on = 0;
     ncclComm_t comm = nullptr;
-    // direct halo exchange over peer memory (kernels_wg.cuh: WgP2P).  p2p_mem = [4 KB flags][halo buffer 0][halo buffer 1]
+    // direct halo exchange over peer memory (kernels_wg.cuh: WgP2P).  p2p_mem = [face flags 0][face flags 1][halo buffer 0][halo buffer 1]
     bool p2p = false;
     DevBuf<unsigned char> p2p_mem;
-    size_t p2p_hb = 0;                               // bytes of one halo buffer (128-byte multiple)
+    size_t p2p_hb = 0, p2p_fb = 0;                   // bytes of one halo buffer / of one per-face flag array (128-byte multiples)
     void *p2p_peer_base[P2P_MAXPEERS] = {};          // peers' p2p_mem, mapped with cudaIpcOpenMemHandle
-    size_t p2p_peer_hb[P2P_MAXPEERS] = {};
+    size_t p2p_peer_hb[P2P_MAXPEERS] = {}, p2p_peer_fb[P2P_MAXPEERS] = {};
     unsigned long long epoch = 0;                    // exchanges produced so far (all ranks run the same sequence)
     const double *pushed = nullptr;                  // vector whose traces exchange `epoch` carries (nullptr: none valid)
-    DevBuf<unsigned int> p2p_done;
     DevBuf<int> p2p_err;
     DevBuf<int> hpush, dgid, dlidx;                  // dgid: local element -> caller's element index (H.elem_gid); dlidx: -> its rank among the owned elements by global id
     long long launches = 0;
@@ -244,19 +243,20 @@ static void exchange(dgtd_ctx *c, const double *y)
 // min) or all stay on the NCCL send/recv path.  DGTD_B200_HALO=nccl forces the latter.
 static void p2p_setup(dgtd_ctx *c)
 {
-    struct Card { cudaIpcMemHandle_t h; unsigned long long hb; unsigned long long ok; char pad[128 - sizeof(cudaIpcMemHandle_t) - 16]; };
+    struct Card { cudaIpcMemHandle_t h; unsigned long long hb; unsigned long long ok; unsigned long long fb; char pad[128 - sizeof(cudaIpcMemHandle_t) - 24]; };
     static_assert(sizeof(Card) == 128, "card size");
     const char *env = std::getenv("DGTD_B200_HALO");
     int want = c->wg && c->nranks <= 512 && (int)c->H.peers.size() <= P2P_MAXPEERS && !(env && std::string(env) == "nccl");
     Card mine{};
     if (want) {
         c->p2p_hb = (((size_t)c->H.n_halo_faces * c->H.Nfp * 6 * sizeof(double)) + 127) / 128 * 128;
-        c->p2p_mem.alloc(4096 + 2 * c->p2p_hb + 128);
+        c->p2p_fb = (((size_t)c->H.n_halo_faces * sizeof(unsigned long long)) + 127) / 128 * 128;
+        c->p2p_mem.alloc(2 * c->p2p_fb + 2 * c->p2p_hb + 128);
         CU(cudaMemset(c->p2p_mem.p, 0, c->p2p_mem.n));
-        c->p2p_done.alloc(1); c->p2p_err.alloc(1);
-        CU(cudaMemset(c->p2p_done.p, 0, sizeof(unsigned int))); CU(cudaMemset(c->p2p_err.p, 0, sizeof(int)));
+        c->p2p_err.alloc(1);
+        CU(cudaMemset(c->p2p_err.p, 0, sizeof(int)));
         if (cudaIpcGetMemHandle(&mine.h, c->p2p_mem.p) != cudaSuccess) { cudaGetLastError(); want = 0; }
-        mine.hb = c->p2p_hb;
+        mine.hb = c->p2p_hb; mine.fb = c->p2p_fb;
     }
     mine.ok = (unsigned long long)want;
     DevBuf<unsigned char> dsend, drecv;
@@ -272,7 +272,7 @@ static void p2p_setup(dgtd_ctx *c)
         for (size_t p = 0; p < c->H.peers.size(); p++) {
             const Card &cd = all[(size_t)c->H.peers[p].rank];
             if (cudaIpcOpenMemHandle(&c->p2p_peer_base[p], cd.h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); c->p2p_peer_base[p] = nullptr; ok = 0; break; }
-            c->p2p_peer_hb[p] = (size_t)cd.hb;
+            c->p2p_peer_hb[p] = (size_t)cd.hb; c->p2p_peer_fb[p] = (size_t)cd.fb;
         }
     // collective verdict
     DevBuf<int> dflag; dflag.alloc(1);
@@ -313,26 +313,26 @@ static void launch_gate(dgtd_ctx *c, const double *ts, int nt)
     c->launches++;
 }
 
-// WgP2P of one launch: consume exchange `wait` from my halo buffers, produce exchange `signal` into the peers'
+// WgP2P of one launch: consume exchange `wait` (my flags and halo buffer of parity wait & 1), produce exchange `signal` into
+// the peers' buffers of parity signal & 1
 static WgP2P p2p_args(dgtd_ctx *c, unsigned long long wait, unsigned long long signal)
 {
     WgP2P q{};
     if (!c->p2p) return q;
     q.hpush = reinterpret_cast<const int2 *>(c->hpush.p);
-    q.npeers = (int)c->H.peers.size();
-    q.flags = reinterpret_cast<const unsigned long long *>(c->p2p_mem.p);
-    for (int p = 0; p < q.npeers; p++) {
+    q.flags = reinterpret_cast<const unsigned long long *>(c->p2p_mem.p + (wait & 1) * c->p2p_fb);
+    for (size_t p = 0; p < c->H.peers.size(); p++) {
         unsigned char *base = static_cast<unsigned char *>(c->p2p_peer_base[p]);
-        q.peer_out[p] = reinterpret_cast<double *>(base + 4096 + (signal & 1) * c->p2p_peer_hb[p]);
-        q.peer_flag[p] = reinterpret_cast<unsigned long long *>(base) + c->H.peers[p].remote_idx;
+        q.peer_flag[p] = reinterpret_cast<unsigned long long *>(base + (signal & 1) * c->p2p_peer_fb[p]);
+        q.peer_out[p] = reinterpret_cast<double *>(base + 2 * c->p2p_peer_fb[p] + (signal & 1) * c->p2p_peer_hb[p]);
     }
     q.wait_epoch = wait; q.signal_epoch = signal;
-    q.done = c->p2p_done.p; q.err = c->p2p_err.p;
+    q.err = c->p2p_err.p;
     return q;
 }
 static const double *p2p_halo_in(dgtd_ctx *c, unsigned long long k)
 {
-    return reinterpret_cast<const double *>(c->p2p_mem.p + 4096 + (k & 1) * c->p2p_hb);
+    return reinterpret_cast<const double *>(c->p2p_mem.p + 2 * c->p2p_fb + (k & 1) * c->p2p_hb);
 }
 
 static void launch_stage(dgtd_ctx *c, int mode, StageArgs &A)
@@ -340,9 +340,9 @@ static void launch_stage(dgtd_ctx *c, int mode, StageArgs &A)
     const bool p2p = c->p2p && c->H.n_halo_faces > 0;
     if (p2p) {
         if (c->pushed != A.yin) {   // the traces of y_in are not at the peers yet: stand-alone producer of the next exchange
-            const int nrec = c->H.n_halo_faces * c->H.Nfp;
+            const int nf = c->H.n_halo_faces;
             c->epoch++;
-            halo_push_kernel<<<std::min(296, (nrec + 127) / 128), 128, 0, c->stream>>>(A.yin, c->bsend_off.p, nrec, c->H.Nfp, p2p_args(c, c->epoch - 1, c->epoch));
+            halo_push_kernel<<<std::min(592, (nf + 63) / 64), 64, 0, c->stream>>>(A.yin, c->bsend_off.p, nf, c->H.Nfp, p2p_args(c, c->epoch - 1, c->epoch));
             c->launches++;
             c->pushed = A.yin;
         }

@@ -119,8 +119,14 @@ constexpr int BLK_E = 8;               // elements per group (= DMMA m dimension
 // fscale[4] at 18, 1/det J at 22, det/eps 23, det/mu 24, sigma/eps 25, 1/fscale[4] at 26.  A stride of 30 doubles puts the
 // records of the 8 elements of a group 28 banks apart in shared memory (distinct multiples of 4 banks: conflict-free
 // LDS.128); a stride of 32 would put them all on the same banks, every geometry LDS.128 costing 8 wavefronts instead of 1
-constexpr int WG_GEO = 30;
-constexpr int WG_TABROWS = 72;         // rows of the node tables kept in shared memory (8 own/canonical + neighbour orientations + push rows)
+#ifndef DGTD_WG_GEO
+#define DGTD_WG_GEO 30
+#endif
+constexpr int WG_GEO = DGTD_WG_GEO;
+#ifndef DGTD_WG_TABROWS
+#define DGTD_WG_TABROWS 72
+#endif
+constexpr int WG_TABROWS = DGTD_WG_TABROWS;         // rows of the node tables kept in shared memory (8 own/canonical + neighbour orientations + push rows)
 struct WgPlan {
     int ngroups = 0, NEpad = 0;
     int NT = 0, KSV = 0;               // output n-tiles (the last one is "mixed"), k-steps of the volume contraction

@@ -27,30 +27,36 @@ namespace dgtd {
 
 // Direct halo exchange over NVLink peer memory (one process per GPU, buffers mapped with CUDA IPC): the stage kernel that
 // PRODUCES y_out stores the traces of its partition faces straight into the neighbour rank's halo buffer, and the kernel
-// that CONSUMES them waits, only in the warps that own a partition face, for the neighbour's epoch flag.  Exchange number k
-// uses halo buffer k & 1 on every rank; a rank signals k after ALL its stores of exchange k (every CTA fences system-wide,
-// the last CTA of the grid raises the flags), which is also after its reads of exchange k-1, so two buffers are enough
-// (see capi.cu: p2p_* for the host side).
-// Round 2 tried to raise a peer's flag as soon as the last group touching that peer had stored (per-peer arrival counters,
-// partition-face groups first in the launch): correct on the small fixtures, but at 786 K elements per rank the N-rank run
-// differed from the single-GPU run by 1e-8 .. 1e-5 in every variant of the arrival fence, so the flag stays at
-// the end of the launch, where all stores of the grid are ordered before it by one fence per CTA.
+// that CONSUMES them waits, only in the lanes that own a partition face, for that face's flag.
+// Per-face handshake: exchange number k uses halo buffer k & 1 and flag array k & 1 on every rank.  The lane that stores the
+// Nfp records of a face writes that face's flag = k with a release store AFTER them (same thread: data and flag are
+// ordered by the thread's own release, no ordering between different SMs is relied upon); the lane of the neighbour that
+// owns the same face polls the flag with acquire loads before it reads the records.  Reuse of a buffer is safe pairwise:
+// a lane pushes exchange k+1 of a face only after it has read the neighbour's exchange k of that face, and the neighbour
+// wrote exchange k after reading my exchange k-1 — the data k+1 overwrites.  No grid-wide election, no counters.
+// Round 2 history: one flag per peer raised by the last CTA of the launch (round 1) and per-peer arrival
+// counters both gave N-rank results that differed from the single-GPU run in a handful of elements per step at 786 K
+// elements per rank (bench.py's parity check), although small fixtures and 400-step stress runs passed.
 // Replaces GlobalEvolution.cpp:763-774 (six blocking MPI exchanges of whole neighbour elements per Mult).
 constexpr int P2P_MAXPEERS = 8;
 struct WgP2P {
     const int2 *hpush;                                   // WgPlan::hpush
     double *peer_out[P2P_MAXPEERS];                      // peer's halo buffer of the exchange being produced
-    unsigned long long *peer_flag[P2P_MAXPEERS];         // peer's flag slot for this rank
-    const unsigned long long *flags;                     // my flag slots, one per peer
-    int npeers;
+    unsigned long long *peer_flag[P2P_MAXPEERS];         // peer's per-face flags of that exchange (indexed by the slot on the peer)
+    const unsigned long long *flags;                     // my per-face flags of the exchange being consumed (indexed by my halo slot)
     unsigned long long wait_epoch, signal_epoch;         // 0: nothing to wait for / nothing to produce
-    unsigned int *done;                                  // CTA counter of the last-CTA election
     int *err;                                            // set when a wait timed out
 };
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
 {
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
@@ -63,30 +69,20 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-// lanes 0..npeers-1 of the calling warp wait for their peer's flag; 20 s without progress sets *err and gives up
-__device__ __forceinline__ void p2p_wait(const WgP2P &pp, int lane)
+// wait until the neighbour has delivered exchange wait_epoch of my halo face `slot`: relaxed polls (no L1 invalidation per
+// poll), then one acquire load; 20 s without progress sets *err and gives up
+__device__ __forceinline__ void p2p_wait_face(const WgP2P &pp, int slot)
 {
-    if (lane < pp.npeers) {
+    const unsigned long long *f = pp.flags + slot;
+    if (ld_relaxed_sys(f) < pp.wait_epoch) {
         const unsigned long long t0 = globaltimer_ns();
-        while (ld_acquire_sys(pp.flags + lane) < pp.wait_epoch) {
+        while (ld_relaxed_sys(f) < pp.wait_epoch) {
             if (globaltimer_ns() - t0 > 20000000000ull) { atomicExch(pp.err, 1); break; }
         }
     }
-    __syncwarp();
-}
-// after the last store of the CTA: make them visible system-wide, elect the last CTA of the grid, signal every peer
-__device__ __forceinline__ void p2p_signal(const WgP2P &pp)
-{
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int prev = atomicAdd(pp.done, 1u);
-        if (prev == gridDim.x - 1) {
-            *pp.done = 0;
-            __threadfence_system();
-            for (int p = 0; p < pp.npeers; p++) st_release_sys(pp.peer_flag[p], pp.signal_epoch);
-        }
-    }
+#ifndef DGTD_P2P_NO_ACQUIRE
+    (void)ld_acquire_sys(f);
+#endif
 }
 
 struct WgArgs {
@@ -148,15 +144,27 @@ __device__ __forceinline__ void load_rec(const double *p, double *u)
 }
 // neighbour record whose address space is known per lane: a generic LD whose lanes fall partly into shared memory costs
 // ~8.5 shared-memory wavefronts per instruction against 2 for the same lanes through LDS (profiles/r1_final_stage_wg_ncu_summary.txt)
-__device__ __forceinline__ void load_rec_split(const double *p, bool in_smem, double *u)
+__device__ __forceinline__ void load_rec_split(const double *p, bool in_smem, double *u, bool halo = false)
 {
+#ifdef DGTD_P2P_NO_ACQUIRE
+    if (halo) {      // A/B variant: strong loads of the peer-written records instead of an acquire (and its L1 invalidation) on the flag
+        asm volatile("ld.relaxed.sys.global.v2.f64 {%0,%1}, [%6];\n\tld.relaxed.sys.global.v2.f64 {%2,%3}, [%6+16];\n\tld.relaxed.sys.global.v2.f64 {%4,%5}, [%6+32];"
+                     : "=d"(u[0]), "=d"(u[1]), "=d"(u[2]), "=d"(u[3]), "=d"(u[4]), "=d"(u[5]) : "l"(p) : "memory");
+        return;
+    }
+#endif
     if (in_smem) {
         const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
         asm volatile("ld.shared.v2.f64 {%0,%1}, [%6];\n\tld.shared.v2.f64 {%2,%3}, [%6+16];\n\tld.shared.v2.f64 {%4,%5}, [%6+32];"
                      : "=d"(u[0]), "=d"(u[1]), "=d"(u[2]), "=d"(u[3]), "=d"(u[4]), "=d"(u[5]) : "r"(a));
     } else {
+#ifdef DGTD_NBR_CG
+        asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%6];\n\tld.global.cg.v2.f64 {%2,%3}, [%6+16];\n\tld.global.cg.v2.f64 {%4,%5}, [%6+32];"
+                     : "=d"(u[0]), "=d"(u[1]), "=d"(u[2]), "=d"(u[3]), "=d"(u[4]), "=d"(u[5]) : "l"(p));
+#else
         asm volatile("ld.global.v2.f64 {%0,%1}, [%6];\n\tld.global.v2.f64 {%2,%3}, [%6+16];\n\tld.global.v2.f64 {%4,%5}, [%6+32];"
                      : "=d"(u[0]), "=d"(u[1]), "=d"(u[2]), "=d"(u[3]), "=d"(u[4]), "=d"(u[5]) : "l"(p));
+#endif
     }
 }
 __device__ __forceinline__ void store_rec(double *p, const double *u)
@@ -209,9 +217,12 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
     const int gstride = gridDim.x * B::NW;
     int g = blockIdx.x * B::NW + warp;
     const bool has_work = g < A.ngroups;
-    bool halo_ready = A.pp.wait_epoch == 0;
+
     const uint4 ownrow = sTab[j];
     const bool inject = A.pw_on && (A.gate == nullptr || *A.gate >= 1e-16);
+    // flag of the partition face this lane pushed in an earlier group, not raised yet: the release store waits for the
+    // lane's peer stores to be performed (an NVLink round trip), so it is issued one group later, when they long are
+    unsigned long long *pend_flag = nullptr;
 
 #ifdef DGTD_L2_HINTS
     const uint64_t polKeep = l2_policy_evict_last(), polOnce = l2_policy_evict_first();
@@ -283,10 +294,13 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
             nb_smem = false;
             nbase = A.halo + (size_t)(-2 - info.x) * Nfp * 6;
         }
-        if (!halo_ready && __any_sync(0xffffffffu, info.x < -1)) { p2p_wait(A.pp, lane); halo_ready = true; }
+        if (A.pp.wait_epoch != 0 && __any_sync(0xffffffffu, info.x < -1)) {      // the neighbour's traces of my partition faces
+            if (info.x < -1) p2p_wait_face(A.pp, -2 - info.x);
+            __syncwarp();
+        }
         double uQ[PF + 1][6];
 #pragma unroll
-        for (int q = 0; q < PF; q++) load_rec_split(nbase + tab_byte(nrow, q) * 6, nb_smem, uQ[q]);
+        for (int q = 0; q < PF; q++) load_rec_split(nbase + tab_byte(nrow, q) * 6, nb_smem, uQ[q], info.x < -1);
 
         // ---------------- volume: k~E_c = D_{c+1} u~H_{c+2} - D_{c+2} u~H_{c+1},  k~H likewise from u~E = -J^T E / det ------
         {
@@ -360,7 +374,7 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
                 double uM[6], dU[6];
                 const double *uP = uQ[s % (PF + 1)];
                 load_rec(yrec + tab_byte(ownrow, s) * 6, uM);
-                if (s + PF < Nfp) load_rec_split(nbase + tab_byte(nrow, s + PF) * 6, nb_smem, uQ[(s + PF) % (PF + 1)]);
+                if (s + PF < Nfp) load_rec_split(nbase + tab_byte(nrow, s + PF) * 6, nb_smem, uQ[(s + PF) % (PF + 1)], info.x < -1);
 #pragma unroll
                 for (int c = 0; c < 3; c++) { dU[c] = fma(-se1, uM[c], uP[c]); dU[3 + c] = fma(-sh1, uM[3 + c], uP[3 + c]); }   // u+ - u- (+ c u-)
                 if (TF && tf && inject) {
@@ -466,6 +480,9 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
         }
         fence_async_smem();
         __syncwarp();
+        if (MODE != MODE_MULT && A.pp.signal_epoch != 0 && __any_sync(0xffffffffu, pend_flag != nullptr)) {
+            if (pend_flag) { st_release_sys(pend_flag, A.pp.signal_epoch); pend_flag = nullptr; }
+        }
         if (MODE != MODE_MULT && A.pp.signal_epoch != 0 && info.x < -1) {   // my traces of the new stage vector -> the peer's halo
             const int2 hp = A.pp.hpush[-2 - info.x];
             const uint4 prow = sTab[hp.x >> 8];
@@ -477,6 +494,11 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
                 load_rec(src + tab_byte(prow, m) * 6, r);
                 store_rec(dst + m * 6, r);
             }
+#ifdef DGTD_P2P_IMMEDIATE_FLAG
+            st_release_sys(A.pp.peer_flag[hp.x & 0xff] + hp.y, A.pp.signal_epoch);     // this face of this exchange is complete
+#else
+            pend_flag = A.pp.peer_flag[hp.x & 0xff] + hp.y;                            // raised in the next epilogue, or at the end
+#endif
         }
         if (lane == 0) {
             const size_t goff = (size_t)g * GS;
@@ -490,29 +512,28 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
         __syncwarp();
     }
     if (lane == 0) bulk_wait_all();
-    if (MODE != MODE_MULT && A.pp.signal_epoch != 0) p2p_signal(A.pp);
+    if (MODE != MODE_MULT && pend_flag) st_release_sys(pend_flag, A.pp.signal_epoch);
 }
 
-// Stand-alone producer of an exchange (the state came from the host, or Mult was called on a foreign vector): the traces of
-// `y` (aos layout) go to the peers' halo buffers, then the same last-CTA signal.
-// Flow control: exchange e overwrites the buffer the peers read exchange e-2 from.  A rank signals m only after its reads of
-// every exchange < m (stream order; a stage kernel signals at its end), so every CTA first waits for the peers' flags to
-// reach wait_epoch = e-1 before it stores anything (a rank that runs ahead of a slow neighbour must not clobber the traces
-// that neighbour is still consuming).
-__global__ void halo_push_kernel(const double *y, const long long *send_off, int nrec, int Nfp, const WgP2P pp)
+// Stand-alone producer of an exchange (the state came from the host, or Mult was called on a foreign vector): one thread
+// per partition face copies the traces of `y` (aos layout) into the neighbour's halo buffer and raises that face's flag.
+// Flow control: exchange e overwrites the records the neighbour read for exchange e-2.  The neighbour produces exchange e-1
+// of a face only after it has consumed e-2 of it (stream order, or the read-then-push order inside a stage kernel), so the
+// thread first waits for ITS OWN flag of that face to reach wait_epoch = e-1 (pp.flags = my flags of parity (e-1) & 1): a
+// rank that runs ahead of a slow neighbour cannot clobber traces that neighbour is still consuming.
+__global__ void halo_push_kernel(const double *y, const long long *send_off, int nfaces, int Nfp, const WgP2P pp)
 {
-    if (pp.wait_epoch != 0) {
-        if (threadIdx.x < 32) p2p_wait(pp, threadIdx.x);
-        __syncthreads();
-    }
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nrec; i += gridDim.x * blockDim.x) {
-        const int s = i / Nfp, m = i - s * Nfp;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nfaces; s += gridDim.x * blockDim.x) {
+        if (pp.wait_epoch != 0) p2p_wait_face(pp, s);
         const int2 hp = pp.hpush[s];
-        double r[6];
-        load_rec(y + send_off[i], r);
-        store_rec(pp.peer_out[hp.x & 0xff] + ((size_t)hp.y * Nfp + m) * 6, r);
+        double *dst = pp.peer_out[hp.x & 0xff] + (size_t)hp.y * Nfp * 6;
+        for (int m = 0; m < Nfp; m++) {
+            double r[6];
+            load_rec(y + send_off[(size_t)s * Nfp + m], r);
+            store_rec(dst + m * 6, r);
+        }
+        st_release_sys(pp.peer_flag[hp.x & 0xff] + hp.y, pp.signal_epoch);
     }
-    p2p_signal(pp);
 }
 
 // halo pack of the NCCL send/recv path: send[s][c] = y[send_off[s] + c]  (48-byte node records, receiver's face-node order)

@@ -84,9 +84,10 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
 
     const int gstride = gridDim.x * B::NW, ngroups = A.ngroups * (BLK_E / WH_E);   // WgArgs counts groups of 8
     int g = blockIdx.x * B::NW + warp;
-    bool halo_ready = A.pp.wait_epoch == 0;
+
     const uint4 ownrow = sTab[j];
     const bool inject = A.pw_on && (A.gate == nullptr || *A.gate >= 1e-16);
+    unsigned long long *pend_flag = nullptr;             // see kernels_wg.cuh: the flag of a pushed face is raised one group later
     const double sgn = h ? -1.0 : 1.0;                   // u~_E = -(J/det)^T E feeds the H rows, u~_H = +(J/det)^T H the E rows
 
     auto issue_y = [&](int gg) {
@@ -138,10 +139,13 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
             nb_smem = false;
             nbase = A.halo + (size_t)(-2 - info.x) * Nfp * 6;
         }
-        if (!halo_ready && __any_sync(0xffffffffu, info.x < -1)) { p2p_wait(A.pp, lane); halo_ready = true; }
+        if (A.pp.wait_epoch != 0 && __any_sync(0xffffffffu, info.x < -1)) {      // the neighbour's traces of my partition faces
+            if (info.x < -1) p2p_wait_face(A.pp, -2 - info.x);
+            __syncwarp();
+        }
         double uQ[PF + 1][6];
 #pragma unroll
-        for (int q = 0; q < PF; q++) load_rec_split(nbase + tab_byte(nrow, q) * 6, nb_smem, uQ[q]);
+        for (int q = 0; q < PF; q++) load_rec_split(nbase + tab_byte(nrow, q) * 6, nb_smem, uQ[q], info.x < -1);
 
         // ---------------- volume: my field's k~_c = D_{c+1} u~_{c+2} - D_{c+2} u~_{c+1} of the OTHER field ---------------------
         {
@@ -204,7 +208,7 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
                 double mO[3], mX[3], dO[3], dX[3];
                 load3(mrec + own, mO);
                 load3(mrec + oth, mX);
-                if (s + PF < Nfp) load_rec_split(nbase + tab_byte(nrow, s + PF) * 6, nb_smem, uQ[(s + PF) % (PF + 1)]);
+                if (s + PF < Nfp) load_rec_split(nbase + tab_byte(nrow, s + PF) * 6, nb_smem, uQ[(s + PF) % (PF + 1)], info.x < -1);
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
                     const double pO = h ? uP[3 + c] : uP[c], pX = h ? uP[c] : uP[3 + c];
@@ -294,6 +298,9 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
             }
         fence_async_smem();
         __syncwarp();                                       // complete records in wX / wZ
+        if (MODE != MODE_MULT && A.pp.signal_epoch != 0 && __any_sync(0xffffffffu, pend_flag != nullptr)) {
+            if (pend_flag) { st_release_sys(pend_flag, A.pp.signal_epoch); pend_flag = nullptr; }
+        }
         if (MODE != MODE_MULT && A.pp.signal_epoch != 0 && h == 0 && info.x < -1) {   // the E-row lane of (element, face) ships the whole records
             const int2 hp = A.pp.hpush[-2 - info.x];
             const uint4 prow = sTab[hp.x >> 8];
@@ -305,6 +312,7 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
                 load_rec(src + tab_byte(prow, m) * 6, r);
                 store_rec(dst + m * 6, r);
             }
+            pend_flag = A.pp.peer_flag[hp.x & 0xff] + hp.y;
         }
         if (lane == 0) {
             const size_t goff = (size_t)g * GS;
@@ -318,7 +326,7 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
         __syncwarp();
     }
     if (leader) bulk_wait_all();
-    if (MODE != MODE_MULT && A.pp.signal_epoch != 0) p2p_signal(A.pp);
+    if (MODE != MODE_MULT && pend_flag) st_release_sys(pend_flag, A.pp.signal_epoch);
 }
 
 }  // namespace dgtd
