@@ -160,6 +160,8 @@ struct dgtd_ctx {
     bool wg = false;                 // aos layout + warp-per-group kernel (the state needs a layout conversion at the ABI)
     WgSet wgs{};
     DevBuf<uint8_t> wtab;
+    DevBuf<unsigned int> wwork;       // two group counters of the warp-per-group kernels: a launch draws from one and zeroes the other
+    unsigned wlaunch = 0;
     DevBuf<int> dev2ref;
     bool identity = true;            // local element order == global order (single rank, no reordering)
     long long Nalloc = 0;            // scalar dofs allocated per component (padded to whole groups of 8 elements in the aos layout)
@@ -359,6 +361,10 @@ static void launch_stage(dgtd_ctx *c, int mode, StageArgs &A)
         W.tfsf_xyz = A.tfsf_xyz; W.gate = A.gate; W.halo = A.halo; W.ngroups = c->WP.ngroups; W.has_sigma = c->has_sigma ? 1 : 0;
         W.alpha = A.alpha; W.pw = A.pw; W.pw_on = A.pw_on;
         W.yin = A.yin; W.x = A.x; W.z = A.z; W.yout = A.yout; W.a = A.a; W.b = A.b; W.t = A.t;
+        // dynamic group scheduling on multi-rank contexts (partition-face groups cost more) and for the half-row kernel
+        // (order 4: +3 %); a single rank at order <= 3 keeps the static split (118.6 vs 119.8 G)
+        const bool dyn = c->nranks > 1 || c->wh || std::getenv("DGTD_B200_DYNAMIC") != nullptr;
+        W.work = dyn ? c->wwork.p + (c->wlaunch & 1) : nullptr; W.work_next = c->wwork.p + ((c->wlaunch + 1) & 1); c->wlaunch++;
         c->wgs.fn[mode]<<<c->grid, c->wgs.threads, c->wgs.smem, c->stream>>>(W);
     } else {
         c->ks.fn[mode]<<<c->grid, c->ks.threads, c->ks.smem, c->stream>>>(A);
@@ -611,6 +617,7 @@ int dgtd_create(const dgtd_mesh *mesh, const dgtd_options *o, dgtd_ctx **out)
         c->grid = (int)std::min<long long>((units + nw - 1) / nw, (long long)prop.multiProcessorCount);
         c->bgeo.upload(c->WP.geo); c->bafrag.upload(c->WP.bfrag); c->bdesc.upload(c->WP.desc); c->bsend_off.upload(c->WP.send_off, 1);
         c->wtab.upload(c->WP.tab, 16); c->dev2ref.upload(c->WP.dev2ref); c->hpush.upload(c->WP.hpush, 2);
+        c->wwork.alloc(2); CU(cudaMemset(c->wwork.p, 0, 2 * sizeof(unsigned int)));
     } else {
         if (H.ntab > 256) throw Error(DGTD_ERR_UNSUPPORTED, "too many distinct face orientations for the generic kernel");
         c->Nalloc = c->Nloc;

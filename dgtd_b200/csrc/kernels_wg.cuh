@@ -94,6 +94,7 @@ struct WgArgs {
     const double *tfsf_xyz;
     const double *gate;
     const double *halo;       // [haloFace][Nfp][6]
+    unsigned int *work, *work_next;   // group counter of this launch (groups beyond the first wave), and the next launch's (zeroed here)
     int ngroups;
     int has_sigma;
     double alpha;
@@ -258,9 +259,19 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
     if (lane == 0 && has_work) { issue_y(g); if (LOAD_X) issue_x(g); if (LOAD_Z) issue_z(g); }
     mbar_wait(barF, 0);
 
-    for (int it = 0; g < A.ngroups; g += gstride, it++) {
+    // Groups beyond the first wave are handed out by a counter, not by a fixed stride: a warp that loses time (partition
+    // faces: waits, NVLink stores; boundary groups) then simply takes fewer groups, instead of every launch ending with
+    // the slowest warp's fixed share; the partial last wave of a static split (20.76 groups per warp at the bench size)
+    // disappears too.  The next group is drawn at the top of an iteration, a whole group ahead of its use.
+    if (A.work && blockIdx.x == 0 && tid == 0) *A.work_next = 0;
+    for (int it = 0; g < A.ngroups; it++) {
         const uint32_t par = it & 1;
-        const int gnext = g + gstride < A.ngroups ? g + gstride : -1;
+        int gnext = 0;
+        if (A.work) {
+            if (lane == 0) gnext = gstride + (int)atomicAdd(A.work, 1u);
+            gnext = __shfl_sync(0xffffffffu, gnext, 0);
+        } else gnext = g + gstride;                     // static split (single-rank contexts at order <= 3: measured 1 % faster there)
+        if (gnext >= A.ngroups) gnext = -1;
         const double *ge = wGeo + e * WG_GEO;
         const double *yrec = wY + e * Np * 6;
         mbar_wait(barY, par);
@@ -510,6 +521,7 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
             if (!(LOAD_X || LOAD_Z)) bulk_wait_read();            // the next epilogue writes these buffers again
         }
         __syncwarp();
+        g = gnext < 0 ? A.ngroups : gnext;
     }
     if (lane == 0) bulk_wait_all();
     if (MODE != MODE_MULT && pend_flag) st_release_sys(pend_flag, A.pp.signal_epoch);

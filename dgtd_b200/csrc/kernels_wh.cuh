@@ -105,9 +105,15 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
     if (leader && g < ngroups) { issue_y(g); if (LOAD_X || LOAD_Z) issue_xz(g); }
     mbar_wait(barF, 0);
 
-    for (int it = 0; g < ngroups; g += gstride, it++) {
+    if (A.work && blockIdx.x == 0 && tid == 0) *A.work_next = 0;      // groups beyond the first wave come from a counter (kernels_wg.cuh)
+    for (int it = 0; g < ngroups; it++) {
         const uint32_t par = it & 1;
-        const int gnext = g + gstride < ngroups ? g + gstride : -1;
+        int gnext = 0;
+        if (A.work) {
+            if (lane == 0) gnext = gstride + (int)atomicAdd(A.work, 1u);
+            gnext = __shfl_sync(0xffffffffu, gnext, 0);
+        } else gnext = g + gstride;                     // static split (single-rank contexts at order <= 3: measured 1 % faster there)
+        if (gnext >= ngroups) gnext = -1;
         const double *ge = wGeo + e * WG_GEO;
         const double *yrec = wY + e * Np * 6;
         mbar_wait(barY, par);
@@ -324,6 +330,7 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
             if (!(LOAD_X || LOAD_Z)) bulk_wait_read();
         }
         __syncwarp();
+        g = gnext < 0 ? ngroups : gnext;
     }
     if (leader) bulk_wait_all();
     if (MODE != MODE_MULT && pend_flag) st_release_sys(pend_flag, A.pp.signal_epoch);

@@ -299,7 +299,21 @@ HostOp build_host_op(const Mesh &m, const Options &o)
     for (int e = 0; e < NE; e++) if (part[e] == o.rank) H.elem_gid.push_back(e);
     const int NEloc = H.NEloc = (int)H.elem_gid.size();
     if (NEloc == 0) throw Error(DGTD_ERR_ARG, "rank owns no elements");
-    if (dim == 3) morton_order(m, H.elem_gid);   // locality: consecutive local elements are spatial neighbours
+    if (dim == 3) {
+        // locality: consecutive local elements are spatial neighbours (Morton order).  Elements that own a partition face come
+        // FIRST, in Morton order among themselves: they fill whole groups instead of being scattered over three times as many,
+        // so the per-group cost of the halo hand-shake (acquire load + L1 invalidation, release store) is paid in fewer groups
+        // and at the start of a launch, and their traces are at the neighbours long before the next launch asks for them.
+        std::vector<int> front, rest;
+        for (int e : H.elem_gid) {
+            bool cut = false;
+            for (int f = 0; f < nf; f++) { const int e2 = nbrE[(size_t)e * nf + f]; cut |= e2 >= 0 && part[e2] != o.rank; }
+            (cut ? front : rest).push_back(e);
+        }
+        morton_order(m, front); morton_order(m, rest);
+        H.elem_gid = front;
+        H.elem_gid.insert(H.elem_gid.end(), rest.begin(), rest.end());
+    }
     for (int le = 0; le < NEloc; le++) g2l[H.elem_gid[le]] = le;
     // shared faces, ordered per peer by (owner-of-lower-rank element id, its face): both sides enumerate identically
     struct Shared { int peer, keyE, keyF, le, f, ge2, f2; };
