@@ -80,9 +80,7 @@ __device__ __forceinline__ void p2p_wait_face(const WgP2P &pp, int slot)
             if (globaltimer_ns() - t0 > 20000000000ull) { atomicExch(pp.err, 1); break; }
         }
     }
-#ifndef DGTD_P2P_NO_ACQUIRE
     (void)ld_acquire_sys(f);
-#endif
 }
 
 struct WgArgs {
@@ -145,27 +143,15 @@ __device__ __forceinline__ void load_rec(const double *p, double *u)
 }
 // neighbour record whose address space is known per lane: a generic LD whose lanes fall partly into shared memory costs
 // ~8.5 shared-memory wavefronts per instruction against 2 for the same lanes through LDS (profiles/r1_final_stage_wg_ncu_summary.txt)
-__device__ __forceinline__ void load_rec_split(const double *p, bool in_smem, double *u, bool halo = false)
+__device__ __forceinline__ void load_rec_split(const double *p, bool in_smem, double *u)
 {
-#ifdef DGTD_P2P_NO_ACQUIRE
-    if (halo) {      // A/B variant: strong loads of the peer-written records instead of an acquire (and its L1 invalidation) on the flag
-        asm volatile("ld.relaxed.sys.global.v2.f64 {%0,%1}, [%6];\n\tld.relaxed.sys.global.v2.f64 {%2,%3}, [%6+16];\n\tld.relaxed.sys.global.v2.f64 {%4,%5}, [%6+32];"
-                     : "=d"(u[0]), "=d"(u[1]), "=d"(u[2]), "=d"(u[3]), "=d"(u[4]), "=d"(u[5]) : "l"(p) : "memory");
-        return;
-    }
-#endif
     if (in_smem) {
         const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
         asm volatile("ld.shared.v2.f64 {%0,%1}, [%6];\n\tld.shared.v2.f64 {%2,%3}, [%6+16];\n\tld.shared.v2.f64 {%4,%5}, [%6+32];"
                      : "=d"(u[0]), "=d"(u[1]), "=d"(u[2]), "=d"(u[3]), "=d"(u[4]), "=d"(u[5]) : "r"(a));
     } else {
-#ifdef DGTD_NBR_CG
-        asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%6];\n\tld.global.cg.v2.f64 {%2,%3}, [%6+16];\n\tld.global.cg.v2.f64 {%4,%5}, [%6+32];"
-                     : "=d"(u[0]), "=d"(u[1]), "=d"(u[2]), "=d"(u[3]), "=d"(u[4]), "=d"(u[5]) : "l"(p));
-#else
         asm volatile("ld.global.v2.f64 {%0,%1}, [%6];\n\tld.global.v2.f64 {%2,%3}, [%6+16];\n\tld.global.v2.f64 {%4,%5}, [%6+32];"
                      : "=d"(u[0]), "=d"(u[1]), "=d"(u[2]), "=d"(u[3]), "=d"(u[4]), "=d"(u[5]) : "l"(p));
-#endif
     }
 }
 __device__ __forceinline__ void store_rec(double *p, const double *u)
@@ -225,35 +211,19 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
     // lane's peer stores to be performed (an NVLink round trip), so it is issued one group later, when they long are
     unsigned long long *pend_flag = nullptr;
 
-#ifdef DGTD_L2_HINTS
-    const uint64_t polKeep = l2_policy_evict_last(), polOnce = l2_policy_evict_first();
-#endif
     auto issue_y = [&](int gg) {
         mbar_expect_tx(barY, (uint32_t)(GS * 8 + B::WGEO * 8 + B::WDESC * 4));
         bulk_load(wY, A.yin + (size_t)gg * GS, GS * 8, barY);
-#ifdef DGTD_L2_HINTS
-        bulk_load_hint(wGeo, A.geo + (size_t)gg * B::WGEO, B::WGEO * 8, barY, polKeep);
-        bulk_load_hint(wGeo + B::WGEO, A.desc + (size_t)gg * B::WDESC, B::WDESC * 4, barY, polKeep);
-#else
         bulk_load(wGeo, A.geo + (size_t)gg * B::WGEO, B::WGEO * 8, barY);
         bulk_load(wGeo + B::WGEO, A.desc + (size_t)gg * B::WDESC, B::WDESC * 4, barY);
-#endif
     };
     auto issue_x = [&](int gg) {
         mbar_expect_tx(barX, (uint32_t)(GS * 8));
-#ifdef DGTD_L2_HINTS
-        bulk_load_hint(wX, (MODE == MODE_STAGE1 ? A.yin : A.x) + (size_t)gg * GS, GS * 8, barX, polOnce);
-#else
         bulk_load(wX, (MODE == MODE_STAGE1 ? A.yin : A.x) + (size_t)gg * GS, GS * 8, barX);
-#endif
     };
     auto issue_z = [&](int gg) {
         mbar_expect_tx(barZ, (uint32_t)(GS * 8));
-#ifdef DGTD_L2_HINTS
-        bulk_load_hint(wZ, A.z + (size_t)gg * GS, GS * 8, barZ, polOnce);
-#else
         bulk_load(wZ, A.z + (size_t)gg * GS, GS * 8, barZ);
-#endif
     };
     if (tid == 0) { mbar_expect_tx(barF, (uint32_t)(B::NFR * 32 * 8)); bulk_load(sm, A.bfrag, B::NFR * 32 * 8, barF); }
     if (lane == 0 && has_work) { issue_y(g); if (LOAD_X) issue_x(g); if (LOAD_Z) issue_z(g); }
@@ -311,7 +281,7 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
         }
         double uQ[PF + 1][6];
 #pragma unroll
-        for (int q = 0; q < PF; q++) load_rec_split(nbase + tab_byte(nrow, q) * 6, nb_smem, uQ[q], info.x < -1);
+        for (int q = 0; q < PF; q++) load_rec_split(nbase + tab_byte(nrow, q) * 6, nb_smem, uQ[q]);
 
         // ---------------- volume: k~E_c = D_{c+1} u~H_{c+2} - D_{c+2} u~H_{c+1},  k~H likewise from u~E = -J^T E / det ------
         {
@@ -385,7 +355,7 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
                 double uM[6], dU[6];
                 const double *uP = uQ[s % (PF + 1)];
                 load_rec(yrec + tab_byte(ownrow, s) * 6, uM);
-                if (s + PF < Nfp) load_rec_split(nbase + tab_byte(nrow, s + PF) * 6, nb_smem, uQ[(s + PF) % (PF + 1)], info.x < -1);
+                if (s + PF < Nfp) load_rec_split(nbase + tab_byte(nrow, s + PF) * 6, nb_smem, uQ[(s + PF) % (PF + 1)]);
 #pragma unroll
                 for (int c = 0; c < 3; c++) { dU[c] = fma(-se1, uM[c], uP[c]); dU[3 + c] = fma(-sh1, uM[3 + c], uP[3 + c]); }   // u+ - u- (+ c u-)
                 if (TF && tf && inject) {
@@ -494,22 +464,28 @@ __global__ void __launch_bounds__(Wg<P>::T, 1) stage_wg_kernel(const WgArgs A)
         if (MODE != MODE_MULT && A.pp.signal_epoch != 0 && __any_sync(0xffffffffu, pend_flag != nullptr)) {
             if (pend_flag) { st_release_sys(pend_flag, A.pp.signal_epoch); pend_flag = nullptr; }
         }
-        if (MODE != MODE_MULT && A.pp.signal_epoch != 0 && info.x < -1) {   // my traces of the new stage vector -> the peer's halo
-            const int2 hp = A.pp.hpush[-2 - info.x];
-            const uint4 prow = sTab[hp.x >> 8];
-            double *dst = A.pp.peer_out[hp.x & 0xff] + (size_t)hp.y * Nfp * 6;
-            const double *src = (MODE == MODE_STAGE4 ? wZ : wX) + e * Np * 6;
-#pragma unroll
-            for (int m = 0; m < Nfp; m++) {
-                double r[6];
-                load_rec(src + tab_byte(prow, m) * 6, r);
-                store_rec(dst + m * 6, r);
+        if (MODE != MODE_MULT && A.pp.signal_epoch != 0) {   // my traces of the new stage vector -> the peers' halo buffers
+            // The warp stores one face at a time: its Nfp records are 3 Nfp consecutive 16-byte pieces in the receiver's
+            // node order, piece p by lane p -> one store instruction covers the face's 48 Nfp contiguous bytes (full NVLink
+            // write packets; lane = face with 3 Nfp stores of 16 scattered bytes each costs ten times the requests).
+            unsigned pm = __ballot_sync(0xffffffffu, info.x < -1);
+            int2 hp = make_int2(0, 0);
+            if (info.x < -1) hp = A.pp.hpush[-2 - info.x];
+            const double *srcb = MODE == MODE_STAGE4 ? wZ : wX;
+            while (pm) {
+                const int owner = __ffs(pm) - 1;
+                pm &= pm - 1;
+                const int hx = __shfl_sync(0xffffffffu, hp.x, owner), hy = __shfl_sync(0xffffffffu, hp.y, owner);
+                const uint4 prow = sTab[hx >> 8];
+                double2 *dst = reinterpret_cast<double2 *>(A.pp.peer_out[hx & 0xff] + (size_t)hy * Nfp * 6);
+                const double *src = srcb + (owner >> 2) * Np * 6;
+                for (int p = lane; p < 3 * Nfp; p += 32) {
+                    const int m = p / 3;
+                    dst[p] = *reinterpret_cast<const double2 *>(src + tab_byte(prow, m) * 6 + (p - 3 * m) * 2);
+                }
             }
-#ifdef DGTD_P2P_IMMEDIATE_FLAG
-            st_release_sys(A.pp.peer_flag[hp.x & 0xff] + hp.y, A.pp.signal_epoch);     // this face of this exchange is complete
-#else
-            pend_flag = A.pp.peer_flag[hp.x & 0xff] + hp.y;                            // raised in the next epilogue, or at the end
-#endif
+            __syncwarp();                                                                   // every lane's pieces before the owner's flag
+            if (info.x < -1) pend_flag = A.pp.peer_flag[hp.x & 0xff] + hp.y;               // raised in the next epilogue, or at the end
         }
         if (lane == 0) {
             const size_t goff = (size_t)g * GS;

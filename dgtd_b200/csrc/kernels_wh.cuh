@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
         }
         double uQ[PF + 1][6];
 #pragma unroll
-        for (int q = 0; q < PF; q++) load_rec_split(nbase + tab_byte(nrow, q) * 6, nb_smem, uQ[q], info.x < -1);
+        for (int q = 0; q < PF; q++) load_rec_split(nbase + tab_byte(nrow, q) * 6, nb_smem, uQ[q]);
 
         // ---------------- volume: my field's k~_c = D_{c+1} u~_{c+2} - D_{c+2} u~_{c+1} of the OTHER field ---------------------
         {
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(Wh<P>::T, 1) stage_wh_kernel(const WgArgs A)
                 double mO[3], mX[3], dO[3], dX[3];
                 load3(mrec + own, mO);
                 load3(mrec + oth, mX);
-                if (s + PF < Nfp) load_rec_split(nbase + tab_byte(nrow, s + PF) * 6, nb_smem, uQ[(s + PF) % (PF + 1)], info.x < -1);
+                if (s + PF < Nfp) load_rec_split(nbase + tab_byte(nrow, s + PF) * 6, nb_smem, uQ[(s + PF) % (PF + 1)]);
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
                     const double pO = h ? uP[3 + c] : uP[c], pX = h ? uP[c] : uP[3 + c];

@@ -87,6 +87,60 @@ void morton_order(const Mesh &m, std::vector<int> &ids)
     for (int i = 0; i < n; i++) ids[i] = key[i].second;
 }
 
+// Groups of BLK_E consecutive elements are what one warp carries through a stage (kernels_wg.cuh): a face whose neighbour
+// sits in the same group is served from the warp's own shared-memory buffer instead of L2.  Morton order alone puts 41 % of
+// the faces of a Kuhn box in-group (30 % on a rank's part of a partitioned box); growing each group from a Morton-ordered
+// seed by always adding the unassigned element that shares most faces with the group reaches 50 %.
+// `ids` (Morton-sorted, all with mark[e] == tag) is rewritten: whole groups first, in seed order; elements of groups that
+// could not be filled (islands) are returned in `left`.  `init` pre-seeds groups (partition-face leftovers, see below).
+void grow_groups(const std::vector<int> &nbrE, int nf, std::vector<int> &mark, int tag, const std::vector<int> &pos,
+                 std::vector<int> &ids, std::vector<int> &left, const std::vector<std::vector<int>> &init = {})
+{
+    std::vector<int> out; out.reserve(ids.size());
+    std::vector<std::pair<int, int>> cand;      // (element, faces shared with the group so far)
+    std::vector<int> grp;
+    auto add = [&](int e) {
+        grp.push_back(e); mark[(size_t)e] = -1 - tag;          // assigned
+        for (int f = 0; f < nf; f++) {
+            const int e2 = nbrE[(size_t)e * nf + f];
+            if (e2 < 0 || mark[(size_t)e2] != tag) continue;
+            bool found = false;
+            for (auto &c : cand) if (c.first == e2) { c.second++; found = true; break; }
+            if (!found) cand.push_back({e2, 1});
+        }
+    };
+    auto grow = [&]() {
+        while ((int)grp.size() < BLK_E && !cand.empty()) {
+            size_t best = 0;
+            for (size_t i = 1; i < cand.size(); i++)
+                if (cand[i].second > cand[best].second || (cand[i].second == cand[best].second && pos[(size_t)cand[i].first] < pos[(size_t)cand[best].first])) best = i;
+            const int e = cand[best].first;
+            cand.erase(cand.begin() + (long)best);
+            add(e);
+        }
+    };
+    size_t scan = 0;
+    for (const auto &g0 : init) {               // pre-seeded groups are always emitted, filled from `ids` in order when adjacency runs out
+        grp.clear(); cand.clear();
+        for (int e : g0) { const int keep = mark[(size_t)e]; add(e); mark[(size_t)e] = keep; }
+        grow();
+        while ((int)grp.size() < BLK_E) {
+            while (scan < ids.size() && mark[(size_t)ids[scan]] != tag) scan++;
+            if (scan == ids.size()) break;
+            add(ids[scan]); grow();
+        }
+        out.insert(out.end(), grp.begin(), grp.end());
+    }
+    for (int seed : ids) {
+        if (mark[(size_t)seed] != tag) continue;
+        grp.clear(); cand.clear();
+        add(seed); grow();
+        if ((int)grp.size() == BLK_E) out.insert(out.end(), grp.begin(), grp.end());
+        else for (int e : grp) left.push_back(e);
+    }
+    ids.swap(out);
+}
+
 }  // namespace
 
 void node_coords(const Mesh &m, const RefElem &ref, std::vector<double> &xyz)
@@ -300,17 +354,36 @@ HostOp build_host_op(const Mesh &m, const Options &o)
     const int NEloc = H.NEloc = (int)H.elem_gid.size();
     if (NEloc == 0) throw Error(DGTD_ERR_ARG, "rank owns no elements");
     if (dim == 3) {
-        // locality: consecutive local elements are spatial neighbours (Morton order).  Elements that own a partition face come
-        // FIRST, in Morton order among themselves: they fill whole groups instead of being scattered over three times as many,
-        // so the per-group cost of the halo hand-shake (acquire load + L1 invalidation, release store) is paid in fewer groups
-        // and at the start of a launch, and their traces are at the neighbours long before the next launch asks for them.
+        // locality: groups of BLK_E consecutive local elements share as many faces as possible (grow_groups), groups follow
+        // a Morton curve.  Elements that own a partition face come FIRST, grouped among themselves: they fill whole groups
+        // instead of being scattered over three times as many, so the per-group cost of the halo hand-shake is paid in fewer
+        // groups and at the start of a launch, and their traces are at the neighbours long before the next launch asks.
         std::vector<int> front, rest;
+        std::vector<int> mark((size_t)NE, 0), pos((size_t)NE, 0);          // mark: 1 partition-face element, 2 other owned element
         for (int e : H.elem_gid) {
             bool cut = false;
             for (int f = 0; f < nf; f++) { const int e2 = nbrE[(size_t)e * nf + f]; cut |= e2 >= 0 && part[e2] != o.rank; }
             (cut ? front : rest).push_back(e);
+            mark[(size_t)e] = cut ? 1 : 2;
         }
         morton_order(m, front); morton_order(m, rest);
+        if (std::getenv("DGTD_B200_ORDER") == nullptr || std::string(std::getenv("DGTD_B200_ORDER")) != "morton") {
+            std::vector<int> all(front); all.insert(all.end(), rest.begin(), rest.end());
+            { std::vector<int> t(all); morton_order(m, t); for (size_t i = 0; i < t.size(); i++) pos[(size_t)t[i]] = (int)i; }
+            auto by_pos = [&](int a, int b) { return pos[(size_t)a] < pos[(size_t)b]; };
+            std::vector<int> leftF, leftR, left2;
+            grow_groups(nbrE, nf, mark, 1, pos, front, leftF);
+            std::sort(leftF.begin(), leftF.end(), by_pos);
+            std::vector<std::vector<int>> init;                              // partition-face leftovers: filled up with other elements
+            for (size_t i = 0; i < leftF.size(); i += BLK_E) init.emplace_back(leftF.begin() + (long)i, leftF.begin() + (long)std::min(leftF.size(), i + BLK_E));
+            grow_groups(nbrE, nf, mark, 2, pos, rest, leftR, init);
+            std::sort(leftR.begin(), leftR.end(), by_pos);
+            for (int e : leftR) mark[(size_t)e] = 3;                         // islands: one more pass among themselves
+            grow_groups(nbrE, nf, mark, 3, pos, leftR, left2);
+            std::sort(left2.begin(), left2.end(), by_pos);
+            rest.insert(rest.end(), leftR.begin(), leftR.end());
+            rest.insert(rest.end(), left2.begin(), left2.end());
+        }
         H.elem_gid = front;
         H.elem_gid.insert(H.elem_gid.end(), rest.begin(), rest.end());
     }
