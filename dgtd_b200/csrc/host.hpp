@@ -123,10 +123,13 @@ constexpr int BLK_E = 8;               // elements per group (= DMMA m dimension
 #define DGTD_WG_GEO 30
 #endif
 constexpr int WG_GEO = DGTD_WG_GEO;
+// rows of the node tables kept in shared memory: 8 own / canonical + (my face, neighbour's face, rotation) <= 4 x 4 x 6
+// + push rows (my face in the receiver's order) <= 4 x 6: 128 covers every conforming tetrahedral mesh and partition
+// (72 was too few for the METIS parts of BASELINE config 4's sphere mesh: 76-80 rows, which then ran the generic kernel)
 #ifndef DGTD_WG_TABROWS
-#define DGTD_WG_TABROWS 72
+#define DGTD_WG_TABROWS 128
 #endif
-constexpr int WG_TABROWS = DGTD_WG_TABROWS;         // rows of the node tables kept in shared memory (8 own/canonical + neighbour orientations + push rows)
+constexpr int WG_TABROWS = DGTD_WG_TABROWS;
 struct WgPlan {
     int ngroups = 0, NEpad = 0;
     int NT = 0, KSV = 0;               // output n-tiles (the last one is "mixed"), k-steps of the volume contraction

@@ -296,3 +296,30 @@ def test_gmsh_reader_on_the_reference_config2_mesh():
     O = HesthavenOracle(pb)
     d = dg.setup_query(m, "dims", np.int32, order=3, bdr={1: dg.BC_PMC, 2: dg.BC_PEC, 3: dg.BC_PMC, 4: dg.BC_PEC})
     assert d[5] == O.NE
+
+
+@pytest.mark.parametrize("world", [1, 2, 8])
+def test_unstructured_partitions_fit_the_warp_per_group_kernel(world, monkeypatch):
+    """BASELINE config 4's sphere mesh: every METIS part must fit the node tables the tensor-core kernels keep in shared
+    memory (8 + 4 x 4 x 6 neighbour orientations + 4 x 6 push rows = 128 rows; with 72 rows the parts fell back to the generic
+    kernel and NCCL), and the groups of eight elements must share faces (in-group faces well above plain Morton order's 27 %)."""
+    from golden_io import product_problem, read_fixture
+    arr, meta = read_fixture("config4_rcs_pec_p3")
+    mesh, kw = product_problem(arr, meta)
+    part = mesh.partition(world, "metis") if world > 1 else None
+    monkeypatch.setenv("DGTD_B200_ORDER", "grow")          # the default of multi-rank contexts; a single rank keeps Morton order
+    for r in range(world):
+        q = lambda name, dt: _q(mesh, kw, name, dt, rank=r, nranks=world, partitioning=part)
+        dims = q("wg_dims", np.int32)
+        ngroups, NEpad, ntab = int(dims[0]), int(dims[1]), int(dims[6])
+        assert ntab <= 128
+        nb = q("wg_desc", np.int32).reshape(NEpad, 4, 2)[:, :, 0]
+        gid = q("elem_gid", np.int32)
+        assert len(np.unique(gid)) == len(gid) and NEpad - len(gid) < 8
+        grp = np.arange(NEpad)[:, None] >> 3
+        in_group = ((nb >= 0) & ((nb >> 3) == grp)).sum() / max(1, (nb >= 0).sum())
+        assert in_group > 0.40, in_group
+        # partition-face elements sit at the front of the local numbering
+        cut = (nb < -1).any(axis=1)
+        if cut.any():
+            assert np.nonzero(cut)[0].max() < 8 * ((cut.sum() + 7) // 8) + 8
