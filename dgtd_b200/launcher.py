@@ -9,6 +9,7 @@ JSON keys honoured (src/driver/driver.cpp):
                   relative_permeability, bulk_conductivity}], boundaries [{tags, type PEC | PMC | SMA}]                           :1242-1479
   sources         {type initial, field_type, center, polarization, dimension, magnitude {type gaussian, spread | resonant, modes}}
                   {type planewave, polarization, propagation, tags, magnitude {spread [, mean] [, frequency]}}                    :531-641
+Without `time_step` (or with 0) the step is the reference's estimate (estimate_time_step below, Solver.cpp:175-351; `cfl` honoured).
 Mesh refinement, probes / exporters, SGBC and the implicit integrators stay with the reference's host code (out of the hot path).
 Multi-GPU: launch one process per GPU with torch.distributed.run; the mesh is partitioned with METIS (driver.cpp:1269).
 Output: <out>/SimulationStats/statistics_rank<r>.dat (the keys of Solver::writeSimulationStatistics, Solver.cpp:404-445) and
@@ -29,6 +30,46 @@ def _vec3(v):
     out = np.zeros(3)
     out[:len(v)] = v
     return out
+
+
+def gauss_lobatto_01(order):
+    """The order+1 Gauss-Lobatto points on [0, 1] (the nodes of mfem's L2 GaussLobatto segment, in dof order)."""
+    if order == 0:
+        return np.array([0.5])
+    inner = np.polynomial.legendre.Legendre.basis(order).deriv().roots() if order > 1 else np.zeros(0)
+    return 0.5 * (np.concatenate([[-1.0], np.sort(inner.real), [1.0]]) + 1.0)
+
+
+def estimate_time_step(verts, elems, dim, order, cfl=1.0, operator="global"):
+    """estimateTimeStep of the reference (src/solver/Solver.cpp:175-351) for segment / triangle / tetrahedron meshes, in the
+    reference's normalised units (c = 1): used when solver_options.time_step is absent or 0 (Solver.cpp:110-115).
+      1-D: cfl * (smallest distance between two nodes of an element) / order^1.5                                :311-320
+      2-D, 3-D: cfl * 0.75 * min_e(volume / (sum of face measures / 2)) * rmin * 2/3, rmin = distance between the
+           first two Gauss-Lobatto nodes of a segment of length 2                                       :206-262, 290-300
+      3-D `global`: that / 0.8;  3-D `hesthaven`: cfl / (max fscale * order^2), fscale = 2 |J_face| / |J_elem|  :326-348"""
+    v = np.asarray(verts, float)[:, :3]
+    x = v[np.asarray(elems)]                                             # [NE][dim+1][3]
+    gl = gauss_lobatto_01(order)
+    if dim == 1:
+        h = np.abs(x[:, 1, 0] - x[:, 0, 0]).min()
+        dmin = h if order == 0 else h * np.diff(gl).min()
+        return cfl * (dmin if order == 0 else dmin / order ** 1.5)
+    rmin = 2.0 * (gl[1] - gl[0]) if order > 0 else 2.0
+    if dim == 2:
+        a, b, c = x[:, 0, :2], x[:, 1, :2], x[:, 2, :2]
+        vol = 0.5 * np.abs((b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (b[:, 1] - a[:, 1]) * (c[:, 0] - a[:, 0]))
+        faces = np.linalg.norm(b - a, axis=1) + np.linalg.norm(c - b, axis=1) + np.linalg.norm(a - c, axis=1)
+        return cfl * 0.75 * (vol / (faces / 2.0)).min() * rmin * 2.0 / 3.0
+    e1, e2, e3 = x[:, 1] - x[:, 0], x[:, 2] - x[:, 0], x[:, 3] - x[:, 0]
+    vol = np.abs(np.einsum("ij,ij->i", np.cross(e1, e2), e3)) / 6.0
+    area = np.zeros((len(x), 4))
+    for f in range(4):
+        p = [q for q in range(4) if q != f]
+        area[:, f] = 0.5 * np.linalg.norm(np.cross(x[:, p[1]] - x[:, p[0]], x[:, p[2]] - x[:, p[0]]), axis=1)
+    if operator == "hesthaven":
+        fscale = 2.0 * (2.0 * area) / (6.0 * vol)[:, None]
+        return cfl / (fscale.max() * order * order)
+    return cfl * 0.75 * (vol / (area.sum(axis=1) / 2.0)).min() * rmin * 2.0 / 3.0 / 0.8
 
 
 def build_case(case, base_dir, dg):
@@ -95,9 +136,10 @@ def build_case(case, base_dir, dg):
 
     kw = dict(order=int(so.get("order", 2)), alpha=float(so.get("upwind_alpha", 1.0)), bdr=bdr, tfsf=tfsf, materials=materials,
               planewave=planewave, tfsf_gate=so.get("evolution_operator", "global") != "hesthaven")
-    if "time_step" not in so:
-        raise SystemExit("launcher: solver_options.time_step is required (Solver::estimateTimeStep stays with the reference)")
-    return mesh, kw, float(so["time_step"]), float(so.get("final_time", 2.0)), initial_state
+    dt = float(so.get("time_step", 0.0))
+    if dt == 0.0:                      # automatic time step (driver.cpp:714-726, Solver.cpp:110-115)
+        dt = float(estimate_time_step(v, e, e.shape[1] - 1, kw["order"], float(so.get("cfl", 1.0)), so.get("evolution_operator", "global")))
+    return mesh, kw, dt, float(so.get("final_time", 2.0)), initial_state
 
 
 def write_statistics(path, run_s, final_time, dt, ne_local, avg_h, n_local, device_bytes):

@@ -61,3 +61,34 @@ def test_config1_json_case_runs_and_returns_after_one_period(tmp_path):
     stats = (out / "SimulationStats" / "statistics_rank0.dat").read_text()
     for key in ("Simulation Run Time:", "Final Time:", "Time Step:", "Number of Mesh Elements: 20", "Number of Local Degrees of Freedom: 80"):
         assert key in stats
+
+
+def test_automatic_time_step_follows_the_reference_formulas(tmp_path):
+    """solver_options.time_step absent or 0 -> estimateTimeStep (Solver.cpp:175-351); known answers worked out by hand from
+    those formulas: Gauss-Lobatto points of order 3 on [0,1] are 0, (1 -+ 1/sqrt 5)/2, 1."""
+    import dgtd_b200 as dg
+    from dgtd_b200.launcher import build_case, estimate_time_step, gauss_lobatto_01
+    g3 = (1.0 - 1.0 / np.sqrt(5.0)) / 2.0
+    assert np.allclose(gauss_lobatto_01(3), [0.0, g3, 1.0 - g3, 1.0]) and np.allclose(gauss_lobatto_01(2), [0.0, 0.5, 1.0])
+    assert np.allclose(gauss_lobatto_01(4), [0.0, (1 - np.sqrt(3 / 7)) / 2, 0.5, (1 + np.sqrt(3 / 7)) / 2, 1.0])
+    # 1-D: 20 segments of 0.05, order 3: 0.05 * g3 / 3^1.5 (Solver.cpp:311-320)
+    xs = np.zeros((21, 3)); xs[:, 0] = np.linspace(0.0, 1.0, 21)
+    seg = np.stack([np.arange(20), np.arange(1, 21)], axis=1)
+    assert abs(estimate_time_step(xs, seg, 1, 3) - 0.05 * g3 / 3 ** 1.5) < 1e-15
+    assert abs(estimate_time_step(xs, seg, 1, 3, cfl=0.5) - 0.5 * 0.05 * g3 / 3 ** 1.5) < 1e-15
+    # 2-D: right triangle with legs 1: area 1/2, perimeter 2 + sqrt 2; rmin = 2 g3
+    tri_v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0.0]])
+    want2 = 0.75 * (0.5 / ((2 + np.sqrt(2)) / 2)) * (2 * g3) * 2 / 3
+    assert abs(estimate_time_step(tri_v, np.array([[0, 1, 2]]), 2, 3) - want2) < 1e-15
+    # 3-D: the Kuhn tetrahedron (0,0,0),(1,0,0),(1,1,0),(1,1,1): volume 1/6, two faces of area 1/2 and two of sqrt(2)/2
+    tet_v = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [1, 1, 1.0]])
+    tet = np.array([[0, 1, 2, 3]])
+    want3 = 0.75 * ((1 / 6) / ((1 + np.sqrt(2)) / 2)) * (2 * g3) * 2 / 3 / 0.8
+    assert abs(estimate_time_step(tet_v, tet, 3, 3, operator="global") - want3) < 1e-15
+    # hesthaven in 3-D: fscale = 2 |J_f| / |J_e| = 2 (2 A) / (6 V), largest face sqrt(2)/2 -> 2 sqrt 2; dt = cfl / (fscale p^2)
+    assert abs(estimate_time_step(tet_v, tet, 3, 3, operator="hesthaven") - 1.0 / (2 * np.sqrt(2) * 9)) < 1e-15
+    # through the case parser: config 1 without time_step
+    case = json.loads(json.dumps(CASE_1D_PEC)); del case["solver_options"]["time_step"]
+    path = _write_case(tmp_path, case, "seg1d_config1_pec")
+    _, _, dt, _, _ = build_case(case, str(tmp_path), dg)
+    assert abs(dt - 0.05 * g3 / 3 ** 1.5) < 1e-12
