@@ -236,6 +236,11 @@ class Problem:
     tfsf_tags: tuple = ()
     materials: dict = field(default_factory=dict)     # element attribute -> (eps, mu, sigma)
     planewave: PlaneWave | None = None
+    # "global": coefficients of GlobalEvolution / DGOperatorFactory (what the product computes and the goldens hold);
+    # "hesthaven": the boundary encodings of HesthavenEvolution.cpp:275-313 (SMA jump -u/alpha with the face's alpha kept, so
+    # its centred part is scaled 1/alpha; interior PEC/PMC/SMA jumps (-1,0)/(0,-1)/(-1/2,-1/2) on both sides).  The two agree
+    # for alpha = 1 on meshes without interior boundaries (tests/test_oracle.py); driver.cpp:1596-1598 forbids alpha = 0 there.
+    flavour: str = "global"
 
 
 class HesthavenOracle:
@@ -291,6 +296,7 @@ class HesthavenOracle:
         vmapM = np.zeros((NE, nf, Nfp), np.int64)
         vmapP = np.zeros((NE, nf, Nfp), np.int64)
         bc = np.zeros((NE, nf), np.int32)
+        self.bc_interior = np.zeros((NE, nf), bool)           # boundary condition declared on a face between two elements
         nbr = -np.ones((NE, nf), np.int64)
         face_tag = np.zeros((NE, nf), np.int32)
         for key, sides in faces.items():
@@ -305,6 +311,7 @@ class HesthavenOracle:
                 if len(sides) == 1 or pb.bdr_cond.get(tag, 0):
                     vmapP[e, f] = vmapM[e, f]
                     bc[e, f] = pb.bdr_cond.get(tag, 0)
+                    self.bc_interior[e, f] = len(sides) == 2
                     continue
                 e2, f2 = sides[1 - s]
                 nbr[e, f] = e2
@@ -383,12 +390,23 @@ class HesthavenOracle:
         uP = uf[:, self.vmapP]
         dU = uP - uM
         alpha = np.full((NE, nf), pb.alpha)
-        for code, (ce, ch) in {PEC: (-2.0, 0.0), PMC: (0.0, -2.0), SMA: (-1.0, -1.0)}.items():
+        hest = pb.flavour == "hesthaven"
+        if hest and pb.alpha == 0.0 and (self.bc == SMA).any():
+            raise ValueError("alpha = 0 with SMA boundaries is not defined in the hesthaven flavour (driver.cpp:1596-1598)")
+        sma = -1.0 / pb.alpha if hest and pb.alpha != 0.0 else -1.0   # HesthavenEvolution.cpp:292 vs DGOperatorFactory.h:483-496
+        for code, (ce, ch) in {PEC: (-2.0, 0.0), PMC: (0.0, -2.0), SMA: (sma, sma)}.items():
             m = self.bc == code
             if m.any():
                 dU[:3, m] = ce * uM[:3, m]
                 dU[3:, m] = ch * uM[3:, m]
-        alpha[self.bc == SMA] = 1.0
+        if hest:                                              # interior boundaries, HesthavenEvolution.cpp:308-310
+            for code, (ce, ch) in {PEC: (-1.0, 0.0), PMC: (0.0, -1.0), SMA: (-0.5, -0.5)}.items():
+                m = (self.bc == code) & self.bc_interior
+                if m.any():
+                    dU[:3, m] = ce * uM[:3, m]
+                    dU[3:, m] = ch * uM[3:, m]
+        else:
+            alpha[self.bc == SMA] = 1.0
         if pb.planewave is not None and self.tfsf_face.any() and self.tfsf_gate(t):
             e_i, f_i = np.nonzero(self.tfsf_face)
             pts = self.xyz.reshape(-1, 3)[self.vmapM[e_i, f_i]]          # (nfaces, Nfp, 3)

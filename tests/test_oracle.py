@@ -146,3 +146,60 @@ def test_numpy_oracle_matches_reference_on_baseline_configs(name):
     assert abs(np.linalg.norm(x) / meta["x_final_norm"] - 1.0) < 1e-12
     if meta.get("tfsf"):
         assert meta["tfsf_applied"] > 0          # the plane wave is on the TF/SF surface at t0
+
+
+@pytest.mark.parametrize("name", [n for n in golden_cases() if not n.startswith("ibc")])
+def test_hesthaven_flavour_equals_global_where_the_reference_says_so(name):
+    """the `hesthaven` boundary encodings (HesthavenEvolution.cpp:275-313) and the `global` ones
+    (DGOperatorFactory.h:483-568) give the same operator when alpha = 1, or when no SMA face is present; with SMA and
+    alpha != 1 they differ by the centred part of the SMA faces scaled 1/alpha (HesthavenEvolution.cpp:292), nowhere else."""
+    import dataclasses
+    from oracle.dgtd_oracle import SMA
+    pb, dat = load_golden(name)
+    x = dat["x0_f64"]
+    t0 = dat["meta"]["t0"]
+    Og = HesthavenOracle(pb)
+    has_sma = bool((Og.bc == SMA).any())
+    if pb.alpha == 1.0 or not has_sma:
+        Oh = HesthavenOracle(dataclasses.replace(pb, flavour="hesthaven"))
+        assert rel_l2(Oh.mult(t0, x), Og.mult(t0, x)) < 1e-13
+    for alpha in (0.5, 0.25):
+        pa = dataclasses.replace(pb, alpha=alpha)
+        Og, Oh = HesthavenOracle(pa), HesthavenOracle(dataclasses.replace(pa, flavour="hesthaven"))
+        kg, kh = Og.mult(t0, x).reshape(6, Og.NE, Og.Np), Oh.mult(t0, x).reshape(6, Og.NE, Og.Np)
+        if not has_sma:
+            assert rel_l2(kh, kg) < 1e-13
+            continue
+        # expected difference: on SMA faces dE_h = -E/alpha instead of -E (same for H); the upwind part alpha*dU is the same
+        # (-U in both, since global uses alpha = 1 there), the centred part n x dU picks up (1/alpha - 1) * (-U)
+        uM = x.reshape(6, -1)[:, Og.vmapM]                                   # (6, NE, nf, Nfp)
+        m = (Og.bc == SMA)[None, :, :, None]
+        extra = np.where(m, -(1.0 / alpha - 1.0) * uM, 0.0)
+        n = np.transpose(Og.normal, (2, 0, 1))[:, :, :, None]
+        cross = lambda a, b: np.stack([a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]])
+        sc = 0.5 * Og.fscale[None, :, :, None]
+        dE = np.einsum("fij,cefj->cei", Og.ref.lift, cross(n, extra[3:]) * sc) * Og.inv_eps[None, :, None]
+        dH = np.einsum("fij,cefj->cei", Og.ref.lift, -cross(n, extra[:3]) * sc) * Og.inv_mu[None, :, None]
+        want = kg + np.concatenate([dE, dH])
+        assert rel_l2(kh, want) < 1e-12
+        untouched = ~(Og.bc == SMA).any(axis=1)
+        assert np.abs(kh[:, untouched] - kg[:, untouched]).max() < 1e-12 * max(1.0, np.abs(kg).max())
+
+
+def test_hesthaven_flavour_interior_boundaries_use_half_coefficients():
+    """HesthavenEvolution.cpp:308-310: interior PEC/PMC/SMA jumps are (-1,0)/(0,-1)/(-1/2,-1/2) on both sides, alpha kept;
+    `global` puts a true boundary on each side (jumps (-2,0)/(0,-2)/(-1,-1), SMA with alpha = 1).  For PEC/PMC sheets the
+    hesthaven face flux is therefore exactly half the global one."""
+    import dataclasses
+    from oracle.dgtd_oracle import PMC, SMA
+    pb, dat = load_golden("ibc3d_p2_pec_box")
+    x = dat["x0_f64"]
+    Og, Oh = HesthavenOracle(pb), HesthavenOracle(dataclasses.replace(pb, flavour="hesthaven"))
+    assert Og.bc_interior.any() and (Og.bc[Og.bc_interior] == PEC).all()
+    # reference operator without the sheet's contribution: zero the trace seen by the sheet faces -> flux of those faces only
+    kg, kh = Og.mult(0.0, x), Oh.mult(0.0, x)
+    pb0 = dataclasses.replace(pb, bdr_cond={k: v for k, v in pb.bdr_cond.items()})
+    O0 = HesthavenOracle(pb0)
+    O0.bc = O0.bc.copy(); O0.bc[O0.bc_interior] = 0                    # sheet faces: self-neighbour, no condition -> zero jump
+    k0 = O0.mult(0.0, x)
+    assert rel_l2(kh - k0, 0.5 * (kg - k0)) < 1e-12 and np.abs(kg - k0).max() > 1e-3

@@ -1,8 +1,9 @@
 #!/usr/bin/env python3
-"""Digest an .ncu-rep (one kernel launch): key counters, stall mix, hottest SASS lines.  Usage: ncu_digest.py rep [ntop]"""
+"""Digest one kernel launch of an .ncu-rep: key counters, stall mix, hottest SASS lines.  Usage: ncu_digest.py rep [ntop [launch]]"""
 import csv, subprocess, sys, io
 rep = sys.argv[1]; ntop = int(sys.argv[2]) if len(sys.argv) > 2 else 25
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+sel = ["--launch-skip", sys.argv[3], "--launch-count", "1"] if len(sys.argv) > 3 else []
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"] + sel, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
 want = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
@@ -17,7 +18,7 @@ want = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
 for i, h in enumerate(hdr):
     if any(h == w or (w.endswith('tensor') and h.startswith(w)) or (w.endswith('dmma') and h.startswith(w)) for w in want):
         print(f"{h:88s} {vals[i]:>20s} {units[i]}")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + sel, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 k = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr, data = rows[k], rows[k + 1:]
