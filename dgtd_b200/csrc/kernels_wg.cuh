@@ -28,10 +28,11 @@ namespace dgtd {
 // Direct halo exchange over NVLink peer memory (one process per GPU, buffers mapped with CUDA IPC): the stage kernel that
 // PRODUCES y_out stores the traces of its partition faces straight into the neighbour rank's halo buffer, and the kernel
 // that CONSUMES them waits, only in the lanes that own a partition face, for that face's flag.
-// Per-face handshake: exchange number k uses halo buffer k & 1 and flag array k & 1 on every rank.  The lane that stores the
-// Nfp records of a face writes that face's flag = k with a release store AFTER them (same thread: data and flag are
-// ordered by the thread's own release, no ordering between different SMs is relied upon); the lane of the neighbour that
-// owns the same face polls the flag with acquire loads before it reads the records.  Reuse of a buffer is safe pairwise:
+// Per-face handshake: exchange number k uses halo buffer k & 1 and flag array k & 1 on every rank.  The warp that owns a
+// face stores its Nfp records (lane p the p-th 16-byte piece), synchronises, and the owning lane writes that face's
+// flag = k with a release store AFTER them (data and flag are ordered inside one warp by bar.warp.sync + the lane's
+// release; no ordering between different SMs is relied upon); the lane of the neighbour that owns the same face polls
+// the flag (relaxed polls, then an acquire load) before it reads the records.  Reuse of a buffer is safe pairwise:
 // a lane pushes exchange k+1 of a face only after it has read the neighbour's exchange k of that face, and the neighbour
 // wrote exchange k after reading my exchange k-1 — the data k+1 overwrites.  No grid-wide election, no counters.
 // Round 2 history: one flag per peer raised by the last CTA of the launch (round 1) and per-peer arrival
