@@ -22,6 +22,14 @@
  * [Ex,Ey,Ez,Hx,Hy,Hz] of N doubles, dof = element*Np + local node, MFEM L2
  * Gauss-Lobatto simplex node order (external/mfem-geg/fem/fe/fe_l2.cpp:716-722).
  * There is NO CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Environment variables read by the library (A/B measurements and diagnostics; none is needed in normal use):
+ *   DGTD_B200_KERNEL=wg|wh|generic   force a stage-kernel family (default: wh at order 4, wg below, generic otherwise)
+ *   DGTD_B200_HALO=nccl              force the pack + ncclSend/ncclRecv halo path instead of peer-memory stores
+ *   DGTD_B200_ORDER=morton|grow      local element order (default: Morton on one rank, face-sharing groups on several)
+ *   DGTD_B200_DYNAMIC=1              counter-based group scheduling on a single rank too
+ *   DGTD_B200_METIS_UFACTOR=n        METIS load-imbalance tolerance in 1/1000 (default 2; the reference's is 30)
+ *   DGTD_B200_FACE_ORDER=bank        alternative order of the face steps inside the kernel plan
  */
 #ifndef DGTD_B200_H
 #define DGTD_B200_H
